@@ -1,0 +1,706 @@
+// capi.cu -- C-ABI (include/grape_b200.h) of the B200-native GRAPE gradient engine.
+//
+// Handle = device-resident GrapeWrk (reference src/workspace.jl:78-144): pulse
+// values, propagators, forward storage, chi states, gradient buffers.  One
+// eval_fg call = one H2D copy of the pulse values, a fixed sequence of kernels
+// on one stream, one D2H copy of (G, grad_J_Tb, grad_J_a, J_parts, sums, tau,
+// flags) and one stream synchronisation.
+#include "../../include/grape_b200.h"
+#include "common.cuh"
+#include "reduce.cuh"
+#include "small_n.cuh"
+#include "warp_n.cuh"
+#include "dense.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct grape_b200_handle_impl {
+    DevP p;
+    int path, device;
+    int LNT;
+    cudaStream_t stream;
+    std::string err;
+    std::vector<void*> dev_allocs;
+    // contiguous device output block: grad[3*LNT] | Jparts[3] | sums[4] | (pad) | tau[2K] | flags
+    double* d_out;
+    size_t out_doubles, off_J, off_sums, off_tau, off_flags;
+    double* h_out;      // pinned mirror of d_out
+    double* h_in;       // pinned staging: pulsevals[LNT] | sums[4]
+    double* d_eps_own;  // handle-owned pulse buffer
+    cplx* d_chi_host;   // [K*N] user chi for backward_chi
+    cplx* d_tmp;        // gather scratch
+    size_t tmp_elems;
+    cudaEvent_t ev[8];
+    bool profiling, forward_done, backward_done;
+    double timings[8];
+    int64_t launches;
+    WarpPlan warp;
+    DensePlan dense;
+};
+typedef grape_b200_handle_impl H;
+
+#define CUDA_TRY(h, call)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            char _b[512];                                                                   \
+            snprintf(_b, sizeof _b, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),      \
+                     __FILE__, __LINE__, cudaGetErrorString(_e));                           \
+            (h)->err = _b;                                                                  \
+            return GRAPE_B200_ECUDA;                                                        \
+        }                                                                                   \
+    } while (0)
+
+template <typename T>
+int dev_alloc(H* h, T** ptr, size_t count) {
+    void* q = nullptr;
+    CUDA_TRY(h, cudaMalloc(&q, (count ? count : 1) * sizeof(T)));
+    h->dev_allocs.push_back(q);
+    *ptr = static_cast<T*>(q);
+    return 0;
+}
+template <typename T>
+int dev_upload(H* h, T** ptr, const T* src, size_t count) {
+    int rc = dev_alloc(h, ptr, count);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpy(*ptr, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int choose_path(int N, int requested) {
+    if (requested != GRAPE_B200_PATH_AUTO) return requested;
+    if (N <= 4) return GRAPE_B200_PATH_SMALL;
+    if (N <= WARP_MAX_N) return GRAPE_B200_PATH_WARP;
+    return GRAPE_B200_PATH_DENSE;
+}
+
+// ------------------------------------------------------------------ small path
+constexpr int SMALL_D = 8;   // cp.async ring depth
+
+int small_bd(const H* h) { return h->p.K <= 16384 ? 32 : 64; }
+size_t small_smem(const H* h) {
+    return (size_t)SMALL_D * h->p.N * h->p.N * sizeof(cplx) * small_bd(h);
+}
+
+template <int N>
+int small_set_attrs(H* h) {
+    const int smem = (int)small_smem(h);
+    CUDA_TRY(h, cudaFuncSetAttribute(small_forward<N, SMALL_D>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(h, cudaFuncSetAttribute(small_backward<N, SMALL_D>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return 0;
+}
+
+int small_setup(H* h, const grape_b200_problem* d) {
+    DevP& p = h->p;
+    const int K = p.K, N = p.N, L = p.L, NT = p.NT, G = p.G, NN = N * N;
+    std::vector<cplx> buf;
+    // H0s[c][g], c = i*N+j ; ABI: H0[g][j*N+i]
+    buf.assign((size_t)NN * G, mk(0, 0));
+    for (int g = 0; g < G; ++g)
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                const double* s = d->H0 + 2 * ((size_t)g * NN + (size_t)j * N + i);
+                buf[(size_t)(i * N + j) * G + g] = mk(s[0], s[1]);
+            }
+    cplx* q;
+    if (int rc = dev_upload(h, &q, buf.data(), buf.size())) return rc;
+    p.H0 = q;
+    buf.assign((size_t)L * NN * G, mk(0, 0));
+    for (int g = 0; g < G; ++g)
+        for (int l = 0; l < L; ++l)
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) {
+                    const double* s = d->Hc + 2 * (((size_t)g * L + l) * NN + (size_t)j * N + i);
+                    buf[((size_t)l * NN + i * N + j) * G + g] = mk(s[0], s[1]);
+                }
+    if (int rc = dev_upload(h, &q, buf.data(), buf.size())) return rc;
+    p.Hc = q;
+    auto soa_states = [&](const double* src, const cplx** dst) -> int {
+        std::vector<cplx> b((size_t)N * K);
+        for (int k = 0; k < K; ++k)
+            for (int i = 0; i < N; ++i) b[(size_t)i * K + k] = mk(src[2 * ((size_t)k * N + i)], src[2 * ((size_t)k * N + i) + 1]);
+        cplx* qq;
+        if (int rc = dev_upload(h, &qq, b.data(), b.size())) return rc;
+        *dst = qq;
+        return 0;
+    };
+    if (int rc = soa_states(d->psi0, &p.psi0)) return rc;
+    if (int rc = soa_states(d->tgt, &p.tgt)) return rc;
+    if (p.gb_kind) {
+        const int nD = p.gb_nD;
+        buf.assign((size_t)NN * nD, mk(0, 0));
+        for (int dd = 0; dd < nD; ++dd)
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) {
+                    const double* s = d->gb_D + 2 * ((size_t)dd * NN + (size_t)j * N + i);
+                    buf[(size_t)(i * N + j) * nD + dd] = mk(s[0], s[1]);
+                }
+        if (int rc = dev_upload(h, &q, buf.data(), buf.size())) return rc;
+        p.D = q;
+    }
+    if (int rc = dev_alloc(h, &p.U, (size_t)NT * NN * G)) return rc;
+    if (int rc = dev_alloc(h, &p.psi, (size_t)(NT + 1) * N * K)) return rc;
+    if (int rc = dev_alloc(h, &p.chi, (size_t)(NT + 1) * N * K)) return rc;
+    int BK = 1;
+    while (BK < K && BK < 128) BK <<= 1;
+    p.KB = (K + BK - 1) / BK;
+    if (int rc = dev_alloc(h, &p.partial, (size_t)p.KB * L * NT)) return rc;
+    switch (N) {
+        case 1: return small_set_attrs<1>(h);
+        case 2: return small_set_attrs<2>(h);
+        case 3: return small_set_attrs<3>(h);
+        case 4: return small_set_attrs<4>(h);
+    }
+    h->err = "small path requires N <= 4";
+    return GRAPE_B200_EINVAL;
+}
+
+template <int N>
+void small_formU_t(H* h) {
+    const long long tot = (long long)h->p.G * h->p.NT;
+    small_form_U<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p);
+    h->launches++;
+}
+template <int N>
+void small_forward_t(H* h) {
+    const int bd = small_bd(h);
+    small_forward<N, SMALL_D><<<(h->p.K + bd - 1) / bd, bd, small_smem(h), h->stream>>>(h->p);
+    h->launches++;
+}
+template <int N>
+void small_backward_t(H* h, const cplx* chi_host) {
+    const int bd = small_bd(h);
+    small_backward<N, SMALL_D><<<(h->p.K + bd - 1) / bd, bd, small_smem(h), h->stream>>>(h->p, chi_host);
+    h->launches++;
+}
+template <int N, int LCMAX>
+void small_gradient_t(H* h) {
+    const DevP& p = h->p;
+    int BK = 1;
+    while (BK < p.K && BK < 128) BK <<= 1;
+    const int BN = 128 / BK;
+    dim3 grid((p.K + BK - 1) / BK, (p.NT + BN - 1) / BN);
+    int l0 = 0;
+    while (l0 < p.L) {
+        const int rem = p.L - l0;
+        if (LCMAX >= 4 && rem >= 4) { small_gradient<N, (LCMAX >= 4 ? 4 : 1)><<<grid, 128, 0, h->stream>>>(p, l0, BK); l0 += 4; }
+        else if (LCMAX >= 2 && rem >= 2) { small_gradient<N, (LCMAX >= 2 ? 2 : 1)><<<grid, 128, 0, h->stream>>>(p, l0, BK); l0 += 2; }
+        else { small_gradient<N, 1><<<grid, 128, 0, h->stream>>>(p, l0, BK); l0 += 1; }
+        h->launches++;
+    }
+}
+
+#define SMALL_DISPATCH(N_, CALL1, CALL2, CALL3, CALL4) \
+    switch (N_) { case 1: CALL1; break; case 2: CALL2; break; case 3: CALL3; break; default: CALL4; break; }
+
+// ------------------------------------------------------------------ phase drivers
+void run_formU(H* h) {
+    switch (h->path) {
+        case GRAPE_B200_PATH_SMALL:
+            SMALL_DISPATCH(h->p.N, small_formU_t<1>(h), small_formU_t<2>(h), small_formU_t<3>(h), small_formU_t<4>(h));
+            break;
+        case GRAPE_B200_PATH_WARP: warp_run_formU(h->warp, h->p, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_DENSE: break;   // dense path never forms U
+    }
+}
+void run_forward(H* h) {
+    switch (h->path) {
+        case GRAPE_B200_PATH_SMALL:
+            SMALL_DISPATCH(h->p.N, small_forward_t<1>(h), small_forward_t<2>(h), small_forward_t<3>(h), small_forward_t<4>(h));
+            break;
+        case GRAPE_B200_PATH_WARP: warp_run_forward(h->warp, h->p, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_DENSE: dense_run_forward(h->dense, h->p, h->stream, h->launches); break;
+    }
+    reduce_tau<<<1, 256, 0, h->stream>>>(h->p);
+    h->launches++;
+}
+void run_backward(H* h, const cplx* chi_host) {
+    switch (h->path) {
+        case GRAPE_B200_PATH_SMALL:
+            SMALL_DISPATCH(h->p.N, small_backward_t<1>(h, chi_host), small_backward_t<2>(h, chi_host),
+                           small_backward_t<3>(h, chi_host), small_backward_t<4>(h, chi_host));
+            break;
+        case GRAPE_B200_PATH_WARP: warp_run_backward(h->warp, h->p, chi_host, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_DENSE: dense_run_backward(h->dense, h->p, chi_host, h->stream, h->launches); break;
+    }
+}
+void run_gradient(H* h) {
+    switch (h->path) {
+        case GRAPE_B200_PATH_SMALL:
+            SMALL_DISPATCH(h->p.N, (small_gradient_t<1, 4>(h)), (small_gradient_t<2, 4>(h)),
+                           (small_gradient_t<3, 2>(h)), (small_gradient_t<4, 1>(h)));
+            break;
+        case GRAPE_B200_PATH_WARP: warp_run_gradient(h->warp, h->p, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_DENSE: break;   // fused into dense_run_backward
+    }
+}
+void run_finalize(H* h, bool grad) {
+    if (grad) {
+        const int blocks = (h->LNT + 255) / 256;
+        finalize_grad<<<blocks < 296 ? blocks : 296, 256, 0, h->stream>>>(h->p);
+        h->launches++;
+    }
+    finalize_J<<<1, 256, 0, h->stream>>>(h->p);
+    h->launches++;
+}
+
+void rec(H* h, int i) {
+    if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
+}
+void collect_timings(H* h, int64_t launches_before) {
+    if (!h->profiling) return;
+    float ms;
+    for (int i = 0; i < 6; ++i) {
+        ms = 0.f;
+        cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]);
+        h->timings[i] = ms;
+    }
+    ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]);
+    h->timings[6] = ms;
+    h->timings[7] = (double)(h->launches - launches_before);
+}
+
+int check_flags(H* h) {
+    const DevFlags* f = reinterpret_cast<const DevFlags*>(h->h_out + h->off_flags);
+    char b[256];
+    if (f->chi_bad_k) {
+        // message of reference src/optimize.jl:1021-1025
+        snprintf(b, sizeof b, "The χ state with index %d has norm %g < %g (chi_min_norm)",
+                 f->chi_bad_k, f->chi_bad_rho, h->p.chi_min_norm);
+        h->err = b;
+        return GRAPE_B200_ECHINORM;
+    }
+    if (f->taylor_fail) {
+        // message of reference src/optimize.jl:644-648
+        snprintf(b, sizeof b, "taylor_grad_step! did not converge within %d iterations. Residual term r=%g.",
+                 h->p.taylor_max_order, f->taylor_r);
+        h->err = b;
+        return GRAPE_B200_ETAYLOR;
+    }
+    return 0;
+}
+
+int upload_pulses(H* h, const double* pulsevals) {
+    memcpy(h->h_in, pulsevals, sizeof(double) * h->LNT);
+    h->p.eps = h->d_eps_own;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_eps_own, h->h_in, sizeof(double) * h->LNT,
+                                cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
+    return 0;
+}
+int download_all(H* h) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * h->out_doubles,
+                                cudaMemcpyDeviceToHost, h->stream));
+    rec(h, 6);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+struct grape_b200_handle : grape_b200_handle_impl {};
+
+extern "C" {
+
+int grape_b200_abi_version(void) { return GRAPE_B200_ABI_VERSION; }
+
+const char* grape_b200_last_error(const grape_b200_handle* h) {
+    return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+void grape_b200_destroy(grape_b200_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    dense_destroy(h->dense);
+    for (void* q : h->dev_allocs) cudaFree(q);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    for (int i = 0; i < 8; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
+    if (!out) return GRAPE_B200_EINVAL;
+    *out = nullptr;
+    auto fail = [&](int code, const std::string& msg) { g_create_error = msg; return code; };
+    if (!d) return fail(GRAPE_B200_EINVAL, "null problem descriptor");
+    if (d->abi_version != GRAPE_B200_ABI_VERSION) return fail(GRAPE_B200_EINVAL, "ABI version mismatch");
+    if (d->L <= 0) return fail(GRAPE_B200_ENOCONTROLS, "no controls in trajectories: cannot optimize");
+    if (d->K <= 0 || d->N <= 0 || d->NT <= 0 || d->G <= 0 || d->G > d->K)
+        return fail(GRAPE_B200_EINVAL, "invalid dimensions (need K,N,NT > 0 and 1 <= G <= K)");
+    if (!d->tlist || !d->H0 || !d->Hc || !d->psi0 || !d->tgt)
+        return fail(GRAPE_B200_EINVAL, "tlist, H0, Hc, psi0 and tgt are required");
+    if (!d->gen_of_traj && d->G != 1 && d->G != d->K)
+        return fail(GRAPE_B200_EINVAL, "gen_of_traj is required unless G == 1 or G == K");
+    if (d->gb_kind != GRAPE_B200_GB_NONE && (!d->gb_D || (d->gb_nD != 1 && d->gb_nD != d->K)))
+        return fail(GRAPE_B200_EINVAL, "g_b quadratic form needs gb_D with gb_nD == 1 or K");
+    if (d->functional < 0 || d->functional > 3 || d->gradient_method < 0 || d->gradient_method > 1)
+        return fail(GRAPE_B200_EINVAL, "invalid functional / gradient_method");
+    for (int n = 0; n < d->NT; ++n)
+        if (!(d->tlist[n + 1] > d->tlist[n])) return fail(GRAPE_B200_EINVAL, "tlist must be strictly increasing");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(GRAPE_B200_ECUDA, std::string("no CUDA device available (") +
+                                          cudaGetErrorString(ce) + "); this engine has no CPU fallback");
+    if (d->device < 0 || d->device >= ndev) return fail(GRAPE_B200_EINVAL, "invalid device ordinal");
+
+    grape_b200_handle* h = new grape_b200_handle();
+    memset(&h->p, 0, sizeof(DevP));
+    h->d_out = nullptr; h->h_out = nullptr; h->h_in = nullptr; h->d_chi_host = nullptr;
+    h->d_tmp = nullptr; h->tmp_elems = 0; h->stream = nullptr;
+    for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
+    h->profiling = false; h->forward_done = false; h->backward_done = false; h->launches = 0;
+    h->device = d->device;
+    auto bail = [&](int rc) {
+        g_create_error = h->err;
+        grape_b200_destroy(h);
+        return rc;
+    };
+#define TRYC(call) do { int _rc = (call); if (_rc) return bail(_rc); } while (0)
+#define CUDA_TRYC(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { h->err = std::string("CUDA error: ") + cudaGetErrorString(_e); return bail(GRAPE_B200_ECUDA); } } while (0)
+    CUDA_TRYC(cudaSetDevice(d->device));
+    CUDA_TRYC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) CUDA_TRYC(cudaEventCreate(&h->ev[i]));
+
+    DevP& p = h->p;
+    p.K = d->K; p.N = d->N; p.L = d->L; p.NT = d->NT; p.G = d->G;
+    p.Kglobal = d->K_global > 0 ? d->K_global : d->K;
+    p.functional = d->functional; p.grad_method = d->gradient_method;
+    p.ja_kind = d->ja_kind; p.gb_kind = d->gb_kind; p.gb_nD = d->gb_kind ? d->gb_nD : 1;
+    p.taylor_max_order = d->taylor_max_order > 0 ? d->taylor_max_order : 100;
+    p.taylor_check = d->taylor_check_convergence;
+    p.taylor_tol = d->taylor_tolerance > 0 ? d->taylor_tolerance : 1e-16;
+    p.lambda_a = d->lambda_a; p.lambda_b = d->lambda_b;
+    p.chi_min_norm = d->chi_min_norm > 0 ? d->chi_min_norm : 1e-100;
+    h->LNT = p.L * p.NT;
+    h->path = choose_path(p.N, d->path);
+    if (h->path == GRAPE_B200_PATH_SMALL && p.N > 4) { h->err = "PATH_SMALL requires N <= 4"; return bail(GRAPE_B200_EINVAL); }
+    if (h->path == GRAPE_B200_PATH_WARP && p.N > WARP_MAX_N) { h->err = "PATH_WARP requires N <= 64"; return bail(GRAPE_B200_EINVAL); }
+
+    const int K = p.K, LNT = h->LNT;
+    {
+        double* q;
+        TRYC(dev_upload(h, &q, d->tlist, (size_t)p.NT + 1)); p.tlist = q;
+        TRYC(dev_alloc(h, &h->d_eps_own, (size_t)LNT)); p.eps = h->d_eps_own;
+        if (d->shape) { TRYC(dev_upload(h, &q, d->shape, (size_t)LNT)); p.shape = q; }
+        if (d->weights) { TRYC(dev_upload(h, &q, d->weights, (size_t)K)); p.w = q; }
+        std::vector<int> gen(K);
+        for (int k = 0; k < K; ++k) {
+            gen[k] = d->gen_of_traj ? d->gen_of_traj[k] : (d->G == 1 ? 0 : k);
+            if (gen[k] < 0 || gen[k] >= d->G) { h->err = "gen_of_traj entry out of range"; return bail(GRAPE_B200_EINVAL); }
+        }
+        int* gi;
+        TRYC(dev_upload(h, &gi, gen.data(), (size_t)K)); p.gen = gi;
+    }
+    // output block
+    h->off_J = (size_t)3 * LNT;
+    h->off_sums = h->off_J + 3;
+    h->off_tau = (h->off_sums + 4 + 1) & ~(size_t)1;
+    h->off_flags = h->off_tau + 2 * (size_t)K;
+    h->out_doubles = h->off_flags + (sizeof(DevFlags) + 7) / 8;
+    TRYC(dev_alloc(h, &h->d_out, h->out_doubles));
+    CUDA_TRYC(cudaMemset(h->d_out, 0, sizeof(double) * h->out_doubles));
+    p.grad = h->d_out;
+    p.Jparts = h->d_out + h->off_J;
+    p.sums = h->d_out + h->off_sums;
+    p.tau = reinterpret_cast<cplx*>(h->d_out + h->off_tau);
+    p.flags = reinterpret_cast<DevFlags*>(h->d_out + h->off_flags);
+    CUDA_TRYC(cudaMallocHost(&h->h_out, sizeof(double) * h->out_doubles));
+    CUDA_TRYC(cudaMallocHost(&h->h_in, sizeof(double) * (LNT + 8)));
+    TRYC(dev_alloc(h, &p.rho, (size_t)K));
+    TRYC(dev_alloc(h, &p.jb, (size_t)K));
+    CUDA_TRYC(cudaMemset(p.jb, 0, sizeof(double) * K));
+    TRYC(dev_alloc(h, &p.chiT, (size_t)K * p.N));
+    TRYC(dev_alloc(h, &h->d_chi_host, (size_t)K * p.N));
+
+    int rc = 0;
+    switch (h->path) {
+        case GRAPE_B200_PATH_SMALL: rc = small_setup(h, d); break;
+        case GRAPE_B200_PATH_WARP: {
+            std::string e;
+            rc = warp_setup(h->warp, p, d, h->dev_allocs, e);
+            if (rc) h->err = e;
+            break;
+        }
+        case GRAPE_B200_PATH_DENSE: {
+            std::string e;
+            rc = dense_setup(h->dense, p, d, h->dev_allocs, e);
+            if (rc) h->err = e;
+            break;
+        }
+        default: h->err = "unknown path"; rc = GRAPE_B200_EINVAL;
+    }
+    if (rc) return bail(rc);
+    CUDA_TRYC(cudaDeviceSynchronize());
+    *out = h;
+    return GRAPE_B200_OK;
+#undef TRYC
+#undef CUDA_TRYC
+}
+
+static void copy_out_common(grape_b200_handle* h, double* J_parts, double* tau) {
+    if (J_parts) memcpy(J_parts, h->h_out + h->off_J, 3 * sizeof(double));
+    if (tau) memcpy(tau, h->h_out + h->off_tau, 2 * sizeof(double) * h->p.K);
+}
+
+int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals, double* J_parts, double* tau) {
+    if (!h || !pulsevals) return GRAPE_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t l0 = h->launches;
+    rec(h, 0);
+    if (int rc = upload_pulses(h, pulsevals)) return rc;
+    run_formU(h); rec(h, 1);
+    run_forward(h); rec(h, 2);
+    run_finalize(h, false); rec(h, 3); rec(h, 4); rec(h, 5);
+    if (int rc = download_all(h)) return rc;
+    collect_timings(h, l0);
+    h->forward_done = true; h->backward_done = false;
+    if (h->p.functional == GRAPE_B200_JT_HOST) h->h_out[h->off_J] = 0.0 / 0.0;
+    copy_out_common(h, J_parts, tau);
+    return check_flags(h);
+}
+
+int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G, double* J_parts,
+                       double* tau, double* grad_J_Tb, double* grad_J_a) {
+    if (!h || !pulsevals || !G) return GRAPE_B200_EINVAL;
+    if (h->p.functional == GRAPE_B200_JT_HOST) {
+        h->err = "eval_fg needs a built-in functional; use forward + backward_chi for JT_HOST";
+        return GRAPE_B200_EINVAL;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t l0 = h->launches;
+    rec(h, 0);
+    if (int rc = upload_pulses(h, pulsevals)) return rc;
+    run_formU(h); rec(h, 1);
+    run_forward(h); rec(h, 2);
+    rec(h, 3);
+    run_backward(h, nullptr); rec(h, 4);
+    run_gradient(h);
+    run_finalize(h, true); rec(h, 5);
+    if (int rc = download_all(h)) return rc;
+    collect_timings(h, l0);
+    h->forward_done = true; h->backward_done = true;
+    const int LNT = h->LNT;
+    memcpy(G, h->h_out, sizeof(double) * LNT);
+    if (grad_J_Tb) memcpy(grad_J_Tb, h->h_out + LNT, sizeof(double) * LNT);
+    if (grad_J_a) memcpy(grad_J_a, h->h_out + 2 * LNT, sizeof(double) * LNT);
+    copy_out_common(h, J_parts, tau);
+    return check_flags(h);
+}
+
+int grape_b200_forward(grape_b200_handle* h, const double* pulsevals, double* tau, double* sums) {
+    if (!h || !pulsevals) return GRAPE_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t l0 = h->launches;
+    rec(h, 0);
+    if (int rc = upload_pulses(h, pulsevals)) return rc;
+    run_formU(h); rec(h, 1);
+    run_forward(h); rec(h, 2); rec(h, 3); rec(h, 4); rec(h, 5);
+    // only sums + tau + flags are needed, but one copy of the block is cheapest
+    if (int rc = download_all(h)) return rc;
+    collect_timings(h, l0);
+    h->forward_done = true; h->backward_done = false;
+    if (tau) memcpy(tau, h->h_out + h->off_tau, 2 * sizeof(double) * h->p.K);
+    if (sums) memcpy(sums, h->h_out + h->off_sums, 4 * sizeof(double));
+    return check_flags(h);
+}
+
+static int backward_common(grape_b200_handle* h, const cplx* chi_host, double* G_partial,
+                           double* J_parts, double* J_b_partial, double* grad_J_a) {
+    const int64_t l0 = h->launches;
+    rec(h, 0); rec(h, 1); rec(h, 2); rec(h, 3);
+    run_backward(h, chi_host); rec(h, 4);
+    run_gradient(h);
+    run_finalize(h, true); rec(h, 5);
+    if (int rc = download_all(h)) return rc;
+    collect_timings(h, l0);
+    h->backward_done = true;
+    const int LNT = h->LNT;
+    if (G_partial) memcpy(G_partial, h->h_out + LNT, sizeof(double) * LNT);   // grad_J_Tb partial
+    if (grad_J_a) memcpy(grad_J_a, h->h_out + 2 * LNT, sizeof(double) * LNT);
+    if (J_parts) memcpy(J_parts, h->h_out + h->off_J, 3 * sizeof(double));
+    if (J_b_partial) *J_b_partial = h->h_out[h->off_sums + 3];
+    return check_flags(h);
+}
+
+int grape_b200_backward(grape_b200_handle* h, const double* sums_global, double* G_partial,
+                        double* J_parts, double* grad_J_a) {
+    if (!h || !sums_global) return GRAPE_B200_EINVAL;
+    if (!h->forward_done) { h->err = "grape_b200_backward called before grape_b200_forward"; return GRAPE_B200_ESTATE; }
+    if (h->p.functional == GRAPE_B200_JT_HOST) { h->err = "JT_HOST: use grape_b200_backward_chi"; return GRAPE_B200_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    memcpy(h->h_in + h->LNT, sums_global, 4 * sizeof(double));
+    CUDA_TRY(h, cudaMemcpyAsync(h->p.sums, h->h_in + h->LNT, 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return backward_common(h, nullptr, G_partial, J_parts, nullptr, grad_J_a);
+}
+
+int grape_b200_backward_chi(grape_b200_handle* h, const double* chiT, double* G_partial,
+                            double* J_b_partial, double* grad_J_a) {
+    if (!h || !chiT) return GRAPE_B200_EINVAL;
+    if (!h->forward_done) { h->err = "grape_b200_backward_chi called before grape_b200_forward"; return GRAPE_B200_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_chi_host, chiT, sizeof(cplx) * (size_t)h->p.K * h->p.N,
+                                cudaMemcpyHostToDevice, h->stream));
+    return backward_common(h, h->d_chi_host, G_partial, nullptr, J_b_partial, grad_J_a);
+}
+
+int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, double* d_G, double* d_J_parts) {
+    if (!h || !d_pulsevals) return GRAPE_B200_EINVAL;
+    if (h->p.functional == GRAPE_B200_JT_HOST) { h->err = "eval_fg_device needs a built-in functional"; return GRAPE_B200_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int64_t l0 = h->launches;
+    rec(h, 0);
+    h->p.eps = d_pulsevals;
+    CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
+    run_formU(h); rec(h, 1);
+    run_forward(h); rec(h, 2); rec(h, 3);
+    run_backward(h, nullptr); rec(h, 4);
+    run_gradient(h);
+    run_finalize(h, true); rec(h, 5);
+    if (d_G) CUDA_TRY(h, cudaMemcpyAsync(d_G, h->p.grad, sizeof(double) * h->LNT, cudaMemcpyDeviceToDevice, h->stream));
+    if (d_J_parts) CUDA_TRY(h, cudaMemcpyAsync(d_J_parts, h->p.Jparts, 3 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_out + h->off_flags, h->p.flags, sizeof(DevFlags), cudaMemcpyDeviceToHost, h->stream));
+    rec(h, 6);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    collect_timings(h, l0);
+    h->p.eps = h->d_eps_own;
+    h->forward_done = true; h->backward_done = true;
+    return check_flags(h);
+}
+
+static int ensure_tmp(grape_b200_handle* h, size_t elems) {
+    if (h->tmp_elems >= elems) return 0;
+    cplx* q;
+    if (int rc = dev_alloc(h, &q, elems)) return rc;
+    h->d_tmp = q; h->tmp_elems = elems;
+    return 0;
+}
+
+__global__ void gather_small_states(const cplx* __restrict__ psi, cplx* __restrict__ out, int K, int N, int NT, int k) {
+    // out[n*N + i] = psi[n][i][k]
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (NT + 1) * N) out[idx] = psi[(size_t)idx * K + k];
+}
+__global__ void gather_small_final(const cplx* __restrict__ psi, cplx* __restrict__ out, int K, int N, int NT) {
+    // out[k*N + i] = psi[NT][i][k]
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < K * N) {
+        const int k = idx / N, i = idx % N;
+        out[idx] = psi[((size_t)NT * N + i) * K + k];
+    }
+}
+
+int grape_b200_get_final_states(grape_b200_handle* h, double* out) {
+    if (!h || !out) return GRAPE_B200_EINVAL;
+    if (!h->forward_done) { h->err = "no forward sweep has been run"; return GRAPE_B200_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const DevP& p = h->p;
+    const size_t cnt = (size_t)p.K * p.N;
+    if (int rc = ensure_tmp(h, cnt)) return rc;
+    if (h->path == GRAPE_B200_PATH_SMALL) {
+        gather_small_final<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(p.psi, h->d_tmp, p.K, p.N, p.NT);
+        h->launches++;
+    } else if (h->path == GRAPE_B200_PATH_WARP) {
+        warp_gather_final(h->warp, p, h->d_tmp, h->stream, h->launches);
+    } else {
+        dense_gather_final(h->dense, p, h->d_tmp, h->stream, h->launches);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_tmp, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int grape_b200_get_stored_states(grape_b200_handle* h, int32_t k, double* out) {
+    if (!h || !out || k < 0 || k >= h->p.K) return GRAPE_B200_EINVAL;
+    if (!h->forward_done) { h->err = "no forward sweep has been run"; return GRAPE_B200_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const DevP& p = h->p;
+    const size_t cnt = (size_t)(p.NT + 1) * p.N;
+    if (int rc = ensure_tmp(h, cnt)) return rc;
+    if (h->path == GRAPE_B200_PATH_SMALL) {
+        gather_small_states<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(p.psi, h->d_tmp, p.K, p.N, p.NT, k);
+        h->launches++;
+    } else if (h->path == GRAPE_B200_PATH_WARP) {
+        warp_gather_states(h->warp, p, k, h->d_tmp, h->stream, h->launches);
+    } else {
+        dense_gather_states(h->dense, p, k, h->d_tmp, h->stream, h->launches);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_tmp, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int grape_b200_get_chi_states(grape_b200_handle* h, double* chi, double* norms) {
+    if (!h) return GRAPE_B200_EINVAL;
+    if (!h->backward_done) { h->err = "no backward sweep has been run"; return GRAPE_B200_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (chi) CUDA_TRY(h, cudaMemcpyAsync(chi, h->p.chiT, sizeof(cplx) * (size_t)h->p.K * h->p.N, cudaMemcpyDeviceToHost, h->stream));
+    if (norms) CUDA_TRY(h, cudaMemcpyAsync(norms, h->p.rho, sizeof(double) * h->p.K, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int grape_b200_get_tau_grads(grape_b200_handle* h, int32_t k, double* out) {
+    if (!h || !out || k < 0 || k >= h->p.K) return GRAPE_B200_EINVAL;
+    if (!h->backward_done) { h->err = "no backward sweep has been run"; return GRAPE_B200_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    DevP& p = h->p;
+    const size_t per = (size_t)p.L * p.NT;
+    if (!p.taugrads) {
+        cplx* q;
+        if (int rc = dev_alloc(h, &q, per * p.K)) return rc;
+        p.taugrads = q;
+        // re-run the contraction with the dump enabled (states are still resident)
+        if (h->path == GRAPE_B200_PATH_DENSE) {
+            h->err = "tau_grads dump is not available on the dense path";
+            return GRAPE_B200_EINVAL;
+        }
+        run_gradient(h);
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(out, p.taugrads + (size_t)k * per, per * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int grape_b200_get_timings(grape_b200_handle* h, double* out8) {
+    if (!h || !out8) return GRAPE_B200_EINVAL;
+    memcpy(out8, h->timings, sizeof h->timings);
+    return 0;
+}
+int grape_b200_set_profiling(grape_b200_handle* h, int32_t on) {
+    if (!h) return GRAPE_B200_EINVAL;
+    h->profiling = on != 0;
+    return 0;
+}
+void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which) {
+    if (!h) return nullptr;
+    switch (which) {
+        case 0: return h->p.grad + h->LNT;   // local grad_J_Tb partial
+        case 1: return h->p.sums;
+        case 2: return h->d_eps_own;
+        case 3: return h->p.grad;            // full G
+    }
+    return nullptr;
+}
+void* grape_b200_stream(grape_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t grape_b200_launch_count(const grape_b200_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

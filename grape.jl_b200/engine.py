@@ -1,0 +1,189 @@
+"""GrapeEngine: the device-resident `GrapeWrk` (reference src/workspace.jl:78-362)
+plus `evaluate_functional` / `evaluate_gradient!` (reference
+src/optimize.jl:696-768, 824-1014) as thin calls through the C-ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .problem import GrapeProblem, HOST
+
+
+class GrapeError(RuntimeError):
+    """Raised with the library's message; mirrors the Julia `error(...)` calls of
+    the reference hot path (src/optimize.jl:644-648, 1021-1025; src/workspace.jl:155-157)."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _colmajor(mats):
+    """[..., N, N] NumPy matrices -> contiguous array whose last two axes are
+    stored column-major (the ABI's Julia layout)."""
+    return np.ascontiguousarray(np.swapaxes(mats, -1, -2))
+
+
+class GrapeEngine:
+    def __init__(self, problem: GrapeProblem, device: int = 0):
+        self.lib = _lib.load()
+        p = self.problem = problem
+        self.K, self.N, self.L, self.NT = p.K, p.N, p.L, p.NT
+        self._keep = keep = {}
+        keep["tlist"] = p.tlist
+        keep["H0"] = _colmajor(p.H0)
+        keep["Hc"] = _colmajor(p.Hc)
+        keep["psi0"], keep["tgt"] = p.psi0, p.tgt
+        keep["gen"] = p.gen_of_traj
+        d = _lib.ProblemDesc()
+        d.abi_version = _lib.ABI_VERSION
+        d.K, d.N, d.L, d.NT, d.G = p.K, p.N, p.L, p.NT, p.G
+        d.K_global, d.device = p.K_global, device
+        d.tlist = _dp(keep["tlist"])
+        d.gen_of_traj = keep["gen"].ctypes.data_as(C.POINTER(C.c_int32))
+        d.H0, d.Hc = _dp(keep["H0"].view(np.float64)), _dp(keep["Hc"].view(np.float64))
+        d.shape = _dp(p.shape)
+        d.psi0, d.tgt = _dp(p.psi0.view(np.float64)), _dp(p.tgt.view(np.float64))
+        d.weights = _dp(p.weights)
+        d.functional, d.gradient_method = p.functional, p.gradient_method
+        d.ja_kind, d.gb_kind = p.ja_kind, p.gb_kind
+        d.lambda_a, d.lambda_b = p.lambda_a, p.lambda_b
+        if p.gb_D is not None and p.gb_kind:
+            keep["D"] = _colmajor(p.gb_D)
+            d.gb_D = _dp(keep["D"].view(np.float64))
+            d.gb_nD = p.gb_D.shape[0]
+        d.taylor_max_order = p.taylor_max_order
+        d.taylor_tolerance = p.taylor_tolerance
+        d.taylor_check_convergence = int(p.taylor_check_convergence)
+        d.path = p.path
+        d.chi_min_norm = p.chi_min_norm
+        h = C.c_void_p()
+        rc = self.lib.grape_b200_create(C.byref(d), C.byref(h))
+        if rc != 0:
+            raise GrapeError(rc, (self.lib.grape_b200_last_error(None) or b"").decode())
+        self._h = h
+        LNT = p.L * p.NT
+        # host mirrors of the GrapeWrk fields callbacks read (src/optimize.jl:402-478)
+        self.J_parts = np.zeros(3)
+        self.tau_vals = np.zeros(p.K, dtype=np.complex128)
+        self.grad_J_Tb = np.zeros(LNT)
+        self.grad_J_a = np.zeros(LNT)
+        self.sums = np.zeros(4)
+        self.fg_calls = 0
+        self.f_calls = 0
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.grape_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GrapeError(rc, (self.lib.grape_b200_last_error(self._h) or b"").decode())
+
+    @staticmethod
+    def _pulses(pulsevals, LNT):
+        x = np.ascontiguousarray(pulsevals, dtype=np.float64)
+        if x.shape != (LNT,):
+            raise ValueError(f"pulsevals must have length L*NT = {LNT}")
+        return x
+
+    # -- evaluate_functional (src/optimize.jl:696-768) --------------------------
+    def evaluate_functional(self, pulsevals):
+        x = self._pulses(pulsevals, self.L * self.NT)
+        self._check(self.lib.grape_b200_eval_f(self._h, _dp(x), _dp(self.J_parts),
+                                               _dp(self.tau_vals.view(np.float64))))
+        self.f_calls += 1
+        return float(np.sum(self.J_parts))
+
+    # -- evaluate_gradient! (src/optimize.jl:824-1014) ---------------------------
+    def evaluate_gradient(self, G, pulsevals):
+        x = self._pulses(pulsevals, self.L * self.NT)
+        if not (isinstance(G, np.ndarray) and G.dtype == np.float64 and G.flags.c_contiguous
+                and G.shape == x.shape):
+            raise ValueError("G must be a contiguous float64 array of length L*NT")
+        self._check(self.lib.grape_b200_eval_fg(
+            self._h, _dp(x), _dp(G), _dp(self.J_parts), _dp(self.tau_vals.view(np.float64)),
+            _dp(self.grad_J_Tb), _dp(self.grad_J_a)))
+        self.fg_calls += 1
+        return float(np.sum(self.J_parts))
+
+    # -- split form --------------------------------------------------------------
+    def forward(self, pulsevals):
+        x = self._pulses(pulsevals, self.L * self.NT)
+        self._check(self.lib.grape_b200_forward(self._h, _dp(x), _dp(self.tau_vals.view(np.float64)),
+                                                _dp(self.sums)))
+        return self.sums.copy()
+
+    def backward(self, sums_global, G_partial):
+        s = np.ascontiguousarray(sums_global, dtype=np.float64)
+        self._check(self.lib.grape_b200_backward(self._h, _dp(s), _dp(G_partial), _dp(self.J_parts),
+                                                 _dp(self.grad_J_a)))
+        return self.J_parts.copy()
+
+    def backward_chi(self, chiT, G_partial):
+        c = np.ascontiguousarray(chiT, dtype=np.complex128)
+        assert c.shape == (self.K, self.N)
+        jb = C.c_double(0.0)
+        self._check(self.lib.grape_b200_backward_chi(self._h, _dp(c.view(np.float64)), _dp(G_partial),
+                                                     C.byref(jb), _dp(self.grad_J_a)))
+        return jb.value
+
+    # -- workspace read-backs ------------------------------------------------------
+    def final_states(self):
+        out = np.zeros((self.K, self.N), dtype=np.complex128)
+        self._check(self.lib.grape_b200_get_final_states(self._h, _dp(out.view(np.float64))))
+        return out
+
+    def stored_states(self, k):
+        """fw_storage[k] as an [N, NT+1] array (column n = Psi_k(t_n))."""
+        out = np.zeros((self.NT + 1, self.N), dtype=np.complex128)
+        self._check(self.lib.grape_b200_get_stored_states(self._h, int(k), _dp(out.view(np.float64))))
+        return out.T
+
+    def chi_states(self):
+        chi = np.zeros((self.K, self.N), dtype=np.complex128)
+        rho = np.zeros(self.K)
+        self._check(self.lib.grape_b200_get_chi_states(self._h, _dp(chi.view(np.float64)), _dp(rho)))
+        return chi, rho
+
+    def tau_grads(self, k):
+        """tau_grads[k] as an [NT, L] complex array (src/workspace.jl:236-237)."""
+        out = np.zeros((self.L, self.NT), dtype=np.complex128)
+        self._check(self.lib.grape_b200_get_tau_grads(self._h, int(k), _dp(out.view(np.float64))))
+        return out.T
+
+    # -- instrumentation -------------------------------------------------------------
+    def set_profiling(self, on=True):
+        self._check(self.lib.grape_b200_set_profiling(self._h, int(bool(on))))
+
+    def timings(self):
+        t = np.zeros(8)
+        self._check(self.lib.grape_b200_get_timings(self._h, _dp(t)))
+        return dict(formU_ms=t[0], forward_ms=t[1], tau_ms=t[2], backward_ms=t[3], gradient_ms=t[4],
+                    d2h_ms=t[5], total_ms=t[6], launches=int(t[7]))
+
+    def launch_count(self):
+        return int(self.lib.grape_b200_launch_count(self._h))
+
+    def eval_fg_device(self, d_pulsevals_ptr, d_G_ptr=None, d_J_ptr=None):
+        self._check(self.lib.grape_b200_eval_fg_device(self._h, d_pulsevals_ptr, d_G_ptr, d_J_ptr))
+
+    def device_ptr(self, which):
+        return self.lib.grape_b200_device_ptr(self._h, which)
+
+    def stream(self):
+        return self.lib.grape_b200_stream(self._h)

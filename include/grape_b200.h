@@ -1,0 +1,186 @@
+/*
+ * grape_b200.h -- C-ABI of the B200-native GRAPE gradient engine.
+ *
+ * Drop-in boundary for the gradient hot path of GRAPE.jl (reference tree at
+ * /root/reference, citations below are relative to it).  The reference's
+ * optimizer back-ends only ever call the closure `fg!(F, G, pulsevals)`
+ * (src/optimize.jl:98-111; invoked at ext/GRAPELBFGSBExt.jl:99 and through
+ * Optim at ext/GRAPEOptimExt.jl:31).  `fg!` is `evaluate_functional`
+ * (src/optimize.jl:696-768) when no gradient is wanted and
+ * `evaluate_gradient!` (src/optimize.jl:824-1014) otherwise, both operating on
+ * the `GrapeWrk` workspace (src/workspace.jl:78-362).  This library replaces
+ * exactly those three things:
+ *
+ *   GrapeWrk(trajectories, tlist, kwargs)   -> grape_b200_create
+ *   evaluate_functional(pulsevals, wrk)     -> grape_b200_eval_f
+ *   evaluate_gradient!(G, pulsevals, wrk)   -> grape_b200_eval_fg
+ *
+ * plus a split form (forward / backward) used when trajectories are sharded
+ * over several processes (one per GPU) or when J_T / chi are arbitrary host
+ * closures, and accessors for the workspace fields that callbacks read
+ * (src/optimize.jl:185-216, 402-478).
+ *
+ * Plain pointers and sizes only; all arrays are caller-owned host memory that
+ * is never retained past the call.  Complex numbers are interleaved
+ * (re, im) doubles = Julia `ComplexF64`.  Matrices are column-major N x N
+ * (Julia layout).  All functions return 0 on success or a GRAPE_B200_E* code;
+ * `grape_b200_last_error` returns the message (the Julia shim turns it into
+ * `error(msg)` so that the catch at src/optimize.jl:125-135 keeps working).
+ *
+ * One handle = one CUDA device = one shard of trajectories.  A handle is not
+ * re-entrant; distinct handles are independent.
+ */
+#ifndef GRAPE_B200_H
+#define GRAPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRAPE_B200_ABI_VERSION 1
+
+/* error codes */
+#define GRAPE_B200_OK            0
+#define GRAPE_B200_EINVAL        1  /* bad descriptor / argument                          */
+#define GRAPE_B200_ECUDA         2  /* CUDA runtime failure (no device, OOM, launch, ...) */
+#define GRAPE_B200_ECHINORM      3  /* chi norm < chi_min_norm (src/optimize.jl:1021-1025) */
+#define GRAPE_B200_ETAYLOR       4  /* taylor_grad_step! did not converge (src/optimize.jl:644-648) */
+#define GRAPE_B200_ENOCONTROLS   5  /* "no controls in trajectories" (src/workspace.jl:155-157) */
+#define GRAPE_B200_ESTATE        6  /* call sequence error (backward before forward, ...)  */
+#define GRAPE_B200_ENCCL         7  /* NCCL failure                                       */
+
+/* J_T / chi kind: QuantumControl.Functionals J_T_sm / J_T_re / J_T_ss with their
+ * analytic chi (make_chi, src/workspace.jl:306-308); HOST = arbitrary closures,
+ * served by grape_b200_forward -> host J_T/chi -> grape_b200_backward_chi. */
+#define GRAPE_B200_JT_SM   0
+#define GRAPE_B200_JT_RE   1
+#define GRAPE_B200_JT_SS   2
+#define GRAPE_B200_JT_HOST 3
+
+/* gradient_method kwarg (src/docstring.jl:108-128) */
+#define GRAPE_B200_GRADGEN 0
+#define GRAPE_B200_TAYLOR  1
+
+/* J_a kind: built-in fluence (J_a_fluence); any other J_a stays a host closure
+ * because it only touches `pulsevals` (src/optimize.jl:761-763, 1004-1011). */
+#define GRAPE_B200_JA_NONE    0
+#define GRAPE_B200_JA_FLUENCE 1
+
+/* g_b kind: built-in quadratic form g_b = <Psi|D|Psi>, xi = -D Psi
+ * (src/optimize.jl:727-750, 856-866, 897-908; test/test_state_running_cost.jl:17-65) */
+#define GRAPE_B200_GB_NONE     0
+#define GRAPE_B200_GB_QUADFORM 1
+
+/* execution path selector (0 = choose from N) */
+#define GRAPE_B200_PATH_AUTO   0
+#define GRAPE_B200_PATH_SMALL  1  /* N <= 4: one thread per (trajectory, step), registers   */
+#define GRAPE_B200_PATH_WARP   2  /* N <= 64: sub-warp per (trajectory, step), shuffles     */
+#define GRAPE_B200_PATH_DENSE  3  /* any N: polynomial apply on state blocks, DMMA ZGEMM    */
+
+/* Problem descriptor = the hot fields of GrapeWrk (src/workspace.jl:78-144). */
+typedef struct grape_b200_problem {
+    int32_t abi_version;      /* GRAPE_B200_ABI_VERSION                                        */
+    int32_t K;                /* trajectories held by THIS handle (local shard)                */
+    int32_t N;                /* Hilbert-space dimension                                       */
+    int32_t L;                /* number of controls                                            */
+    int32_t NT;               /* number of time intervals = length(tlist) - 1                  */
+    int32_t G;                /* number of distinct generators (1 <= G <= K)                   */
+    int32_t K_global;         /* trajectories over all shards (0 -> K); functionals use this   */
+    int32_t device;           /* CUDA device ordinal                                           */
+    const double*  tlist;     /* [NT+1]                                                        */
+    const int32_t* gen_of_traj; /* [K] generator index per trajectory; NULL: 0 if G==1, k if G==K */
+    const double*  H0;        /* [G][N*N] complex, column-major: drift of generator g          */
+    const double*  Hc;        /* [G][L][N*N] complex, column-major: control operators          */
+    const double*  shape;     /* [L][NT] amplitude shape S (ShapedAmplitude) or NULL (= 1)     */
+    const double*  psi0;      /* [K][N] complex initial states                                 */
+    const double*  tgt;       /* [K][N] complex target states                                  */
+    const double*  weights;   /* [K] trajectory weights or NULL (= 1)                          */
+    int32_t functional;       /* GRAPE_B200_JT_*                                               */
+    int32_t gradient_method;  /* GRAPE_B200_GRADGEN / _TAYLOR                                  */
+    int32_t ja_kind;          /* GRAPE_B200_JA_*                                               */
+    int32_t gb_kind;          /* GRAPE_B200_GB_*                                               */
+    double  lambda_a;         /* src/docstring.jl:96                                           */
+    double  lambda_b;         /* src/docstring.jl:104                                          */
+    const double* gb_D;       /* [gb_nD][N*N] complex column-major Hermitian D, or NULL        */
+    int32_t gb_nD;            /* 1 (shared) or K (one per trajectory)                          */
+    int32_t taylor_max_order;         /* taylor_grad_max_order (default 100)                   */
+    double  taylor_tolerance;         /* taylor_grad_tolerance (default 1e-16)                 */
+    int32_t taylor_check_convergence; /* taylor_grad_check_convergence (default 1)             */
+    int32_t path;             /* GRAPE_B200_PATH_*                                             */
+    double  chi_min_norm;     /* default 1e-100 (src/optimize.jl:846)                          */
+} grape_b200_problem;
+
+typedef struct grape_b200_handle grape_b200_handle;
+
+int  grape_b200_abi_version(void);
+
+/* GrapeWrk constructor (src/workspace.jl:147-362): uploads the static problem once. */
+int  grape_b200_create(const grape_b200_problem* desc, grape_b200_handle** out);
+void grape_b200_destroy(grape_b200_handle* h);
+/* h == NULL -> message of the last failed grape_b200_create on this thread */
+const char* grape_b200_last_error(const grape_b200_handle* h);
+
+/* evaluate_functional (src/optimize.jl:696-768).
+ * pulsevals [L*NT] blocked by control (src/workspace.jl:159-162);
+ * J_parts[3] = (J_T, lambda_a*J_a, lambda_b*J_b)  (src/optimize.jl:755-766);
+ * tau [2*K] complex overlaps (src/optimize.jl:753), may be NULL. */
+int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals,
+                      double* J_parts, double* tau);
+
+/* evaluate_gradient! (src/optimize.jl:824-1014).
+ * G [L*NT] full gradient; grad_J_Tb / grad_J_a [L*NT] may be NULL
+ * (wrk.grad_J_Tb, wrk.grad_J_a, src/optimize.jl:1002-1011). */
+int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G,
+                       double* J_parts, double* tau, double* grad_J_Tb, double* grad_J_a);
+
+/* Split form.  forward = src/optimize.jl:696-753 on the local shard.
+ * sums[4] = local partial (Re sum_k w_k tau_k, Im sum_k w_k tau_k,
+ *            sum_k w_k |tau_k|^2, sum_k J_b_trajectory[k]).
+ * The caller all-reduces `sums` over shards (or uses them as they are for one
+ * shard) and passes the global values to grape_b200_backward, which evaluates
+ * chi (src/optimize.jl:845-869), the backward sweep (:873-994) and the
+ * k-reduction (:574-584) for the local trajectories.  G_partial [L*NT] is the
+ * LOCAL partial of grad_J_Tb; the caller sums it over shards and adds
+ * lambda_a*grad_J_a (returned in full by every shard). */
+int grape_b200_forward(grape_b200_handle* h, const double* pulsevals,
+                       double* tau, double* sums);
+int grape_b200_backward(grape_b200_handle* h, const double* sums_global,
+                        double* G_partial, double* J_parts, double* grad_J_a);
+/* HOST functional: caller supplies chi_k(T) = -dJ_T/d<Psi_k(T)|  [K][N] complex,
+ * un-normalised (src/optimize.jl:845-855); J_T itself stays on the host. */
+int grape_b200_backward_chi(grape_b200_handle* h, const double* chiT,
+                            double* G_partial, double* J_b_partial, double* grad_J_a);
+
+/* Workspace read-backs for callbacks / result bookkeeping. */
+int grape_b200_get_final_states(grape_b200_handle* h, double* out /* [K][N] complex */);   /* fw_propagators[k].state, src/optimize.jl:187-189 */
+int grape_b200_get_stored_states(grape_b200_handle* h, int32_t k, double* out /* N x (NT+1) complex col-major */); /* wrk.fw_storage[k], src/workspace.jl:215 */
+int grape_b200_get_chi_states(grape_b200_handle* h, double* chi /* [K][N] complex */, double* norms /* [K] */); /* wrk.chi_states, chi_states_norm src/optimize.jl:867-869 */
+int grape_b200_get_tau_grads(grape_b200_handle* h, int32_t k, double* out /* NT x L complex col-major */);   /* wrk.tau_grads[k], src/workspace.jl:236-237 */
+
+/* Per-phase device timings of the last eval call, milliseconds (CUDA events):
+ * out[0]=H2D+propagator formation, [1]=forward sweep, [2]=tau/chi, [3]=backward sweep,
+ * [4]=gradient contraction+reduction, [5]=D2H, [6]=total device, [7]=kernel launches in the call */
+int grape_b200_get_timings(grape_b200_handle* h, double* out8);
+/* Enable (1) / disable (0) per-phase event timing (adds event records, default off). */
+int grape_b200_set_profiling(grape_b200_handle* h, int32_t on);
+
+/* Device-resident entry points for benchmarks / pipelines: same as eval_fg but
+ * pulsevals and G are DEVICE pointers on the handle's device; nothing is copied
+ * to the host except the error flags.  `stream` is a cudaStream_t (0 = the
+ * handle's own stream). */
+int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, double* d_G,
+                              double* d_J_parts /* 3, device, may be NULL */);
+/* Device pointer of the handle's gradient buffer [L*NT] and sums buffer [4]
+ * (for in-place collectives by the caller). */
+void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which); /* 0: grad partial, 1: sums, 2: pulsevals */
+/* cudaStream_t the handle launches on (so callers can time with events on it). */
+void* grape_b200_stream(grape_b200_handle* h);
+/* number of kernels launched by this handle since creation */
+int64_t grape_b200_launch_count(const grape_b200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPE_B200_H */

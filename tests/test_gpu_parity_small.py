@@ -1,0 +1,182 @@
+"""GPU parity: CUDA small-N path (through the C-ABI) vs the CPU oracle.
+
+Tolerance: north_star asks J_T and every gradient element to 1e-10 relative;
+we test |dG| <= 1e-10 * max|G| (and the same for J) on every case."""
+import numpy as np
+import pytest
+
+import grape.jl_b200 as gb
+from grape.jl_b200 import configs
+from oracle import grape_oracle as go
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def engine(p):
+    from grape.jl_b200.engine import GrapeEngine
+    return GrapeEngine(p)
+
+
+def check(p, eps, rtol=RTOL):
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    e = engine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    scale = max(np.max(np.abs(ref["G"])), 1e-6)   # (N=1 + J_T_ss has an identically zero gradient)
+    assert abs(J - ref["J"]) <= rtol * max(1.0, abs(ref["J"])), (J, ref["J"])
+    assert np.max(np.abs(e.J_parts - ref["J_parts"])) <= rtol * max(1.0, np.max(np.abs(ref["J_parts"])))
+    assert np.max(np.abs(e.tau_vals - ref["tau"])) <= rtol
+    err = np.max(np.abs(G - ref["G"])) / scale
+    assert err <= rtol, f"gradient rel err {err:.3e}"
+    assert np.max(np.abs(e.grad_J_Tb - ref["grad_J_Tb"])) / scale <= rtol
+    assert np.max(np.abs(e.grad_J_a - ref["grad_J_a"])) <= rtol * max(1.0, np.max(np.abs(ref["grad_J_a"])))
+    # functional-only call agrees
+    J2 = e.evaluate_functional(eps)
+    assert abs(J2 - ref["J"]) <= rtol * max(1.0, abs(ref["J"]))
+    return e, ref
+
+
+def test_c1_readme_known_answer(lib_built):
+    p, eps = configs.c1_readme()
+    e, ref = check(p, eps)
+    # analytic Rabi answer, SURVEY 8c (4)
+    om = np.sqrt(1 + 0.2 ** 2)
+    assert abs(e.J_parts[0] - (1 - (0.2 ** 2 / om ** 2) * np.sin(om * 5) ** 2)) < 1e-12
+
+
+def test_tls_fixture(lib_built):
+    p, eps = configs.tls_fixture()
+    check(p, eps)
+
+
+@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
+@pytest.mark.parametrize("N", [1, 2, 3, 4])
+def test_random_small(lib_built, N, functional):
+    p, eps = configs.random_problem(K=5, N=N, L=2, NT=17, seed=10 * N + functional, functional=functional)
+    check(p, eps)
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5, 7])
+def test_control_counts(lib_built, L):
+    p, eps = configs.random_problem(K=3, N=3, L=L, NT=9, seed=100 + L)
+    check(p, eps)
+    p, eps = configs.random_problem(K=3, N=2, L=L, NT=9, seed=200 + L)
+    check(p, eps)
+
+
+def test_non_hermitian_shaped_weighted_shared_generator(lib_built):
+    w = np.array([0.5, 1.5, 1.0, 2.0, 0.25, 0.75, 1.25])
+    p, eps = configs.random_problem(K=7, N=3, L=2, NT=15, G=3, seed=7, hermitian=False, shaped=True,
+                                    weights=w, functional=gb.SM)
+    check(p, eps)
+    p, eps = configs.random_problem(K=7, N=4, L=3, NT=11, G=1, seed=8, hermitian=False, shaped=True,
+                                    weights=w, functional=gb.SS)
+    check(p, eps)
+
+
+def test_large_norm_scaling_and_squaring(lib_built):
+    # ||H dt|| ~ 6: exercises squarings (phase A) and sub-steps (phase C)
+    p, eps = configs.random_problem(K=4, N=3, L=2, NT=6, seed=3, uniform=True)
+    p.tlist = p.tlist * 40.0
+    check(p, eps, rtol=1e-9)
+
+
+def test_running_costs(lib_built):
+    D = np.diag([0.0, 1.0, 0.5]).astype(complex)
+    D[0, 1] = 0.2 - 0.1j
+    D[1, 0] = 0.2 + 0.1j
+    p, eps = configs.random_problem(K=4, N=3, L=2, NT=14, seed=5, functional=gb.SS,
+                                    gb_kind=gb.GB_QUADFORM, gb_D=D, lambda_b=0.4,
+                                    ja_kind=gb.JA_FLUENCE, lambda_a=0.3)
+    e, ref = check(p, eps)
+    assert e.J_parts[2] != 0 and e.J_parts[1] != 0
+    # per-trajectory D
+    Ds = np.stack([D * (1 + 0.1 * k) for k in range(4)])
+    p, eps = configs.random_problem(K=4, N=3, L=2, NT=14, seed=6, functional=gb.SM,
+                                    gb_kind=gb.GB_QUADFORM, gb_D=Ds, lambda_b=0.7)
+    check(p, eps)
+
+
+def test_taylor_method_matches_gradgen(lib_built):
+    # reference test/test_tls_optimization.jl:204-233: |J_T(taylor) - J_T(gradgen)| < 1e-10
+    p, eps = configs.random_problem(K=3, N=3, L=2, NT=12, seed=11, gradient_method=gb.TAYLOR)
+    e, ref = check(p, eps)
+    p2, _ = configs.random_problem(K=3, N=3, L=2, NT=12, seed=11, gradient_method=gb.GRADGEN)
+    G1, G2 = np.zeros_like(eps), np.zeros_like(eps)
+    engine(p).evaluate_gradient(G1, eps)
+    engine(p2).evaluate_gradient(G2, eps)
+    assert np.max(np.abs(G1 - G2)) <= 1e-13 * np.max(np.abs(G2))
+
+
+def test_workspace_readbacks(lib_built):
+    p, eps = configs.random_problem(K=6, N=3, L=2, NT=10, seed=21)
+    e, ref = check(p, eps)
+    G = np.zeros_like(eps)
+    e.evaluate_gradient(G, eps)
+    assert np.max(np.abs(e.final_states() - ref["final_states"])) < 1e-12
+    for k in (0, 3, 5):
+        assert np.max(np.abs(e.stored_states(k) - ref["storage"][k])) < 1e-12
+        assert np.max(np.abs(e.tau_grads(k) - ref["tau_grads"][k])) < 1e-12
+    chi, rho = e.chi_states()
+    assert np.max(np.abs(chi - ref["chi_states"])) < 1e-12
+    assert np.max(np.abs(rho - ref["chi_norms"])) < 1e-12 * np.max(ref["chi_norms"])
+
+
+def test_c3_reduced(lib_built):
+    p, eps = configs.c3_ensemble(n_delta=6, n_amp=7, NT=200)
+    check(p, eps)
+    p, eps = configs.c3_ensemble(n_delta=6, n_amp=7, NT=200, functional=gb.SM)
+    check(p, eps)
+
+
+def test_split_forward_backward_matches_eval_fg(lib_built):
+    p, eps = configs.random_problem(K=9, N=3, L=2, NT=13, seed=31, functional=gb.SM)
+    e = engine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    sums = e.forward(eps)
+    Gp = np.zeros_like(eps)
+    Jp = e.backward(sums, Gp)
+    assert np.array_equal(Gp, G)
+    assert abs(np.sum(Jp) - J) == 0
+
+
+def test_host_functional_round_trip(lib_built):
+    # J_T_ss evaluated by "host closures": forward -> host chi -> backward_chi
+    p, eps = configs.random_problem(K=5, N=3, L=2, NT=13, seed=41, functional=gb.HOST)
+    pr, _ = configs.random_problem(K=5, N=3, L=2, NT=13, seed=41, functional=gb.SS)
+    ref = go.evaluate_gradient(go.from_problem(pr), eps)
+    e = engine(p)
+    e.forward(eps)
+    psiT = e.final_states()
+    tau = np.einsum("ki,ki->k", p.tgt.conj(), psiT)
+    chi = (tau / p.K)[:, None] * p.tgt
+    Gp = np.zeros_like(eps)
+    e.backward_chi(chi, Gp)
+    assert np.max(np.abs(Gp - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+
+
+def test_chi_norm_guard_and_errors(lib_built):
+    from grape.jl_b200.engine import GrapeError
+    # orthogonal final state => sum tau = 0 => chi = 0 => error of optimize.jl:1021-1025
+    p, eps = configs.c1_readme(NT=4)
+    p.H0[:] = 0
+    p.Hc[:] = 0
+    e = engine(p)
+    with pytest.raises(GrapeError, match="chi_min_norm"):
+        e.evaluate_gradient(np.zeros_like(eps), eps)
+    # taylor non-convergence: optimize.jl:644-648
+    p, eps = configs.random_problem(K=2, N=3, L=1, NT=4, seed=1, gradient_method=gb.TAYLOR,
+                                    taylor_max_order=3)
+    with pytest.raises(GrapeError, match="did not converge within 3 iterations"):
+        engine(p).evaluate_gradient(np.zeros_like(eps), eps)
+
+
+def test_deterministic(lib_built):
+    p, eps = configs.c3_ensemble(n_delta=20, n_amp=20, NT=50)
+    e = engine(p)
+    G1, G2 = np.zeros_like(eps), np.zeros_like(eps)
+    e.evaluate_gradient(G1, eps)
+    e.evaluate_gradient(G2, eps)
+    assert np.array_equal(G1, G2)

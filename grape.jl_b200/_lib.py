@@ -54,6 +54,10 @@ SYMBOLS = {
     "grape_b200_get_timings": (C.c_int, [_P, _D]),
     "grape_b200_set_profiling": (C.c_int, [_P, C.c_int32]),
     "grape_b200_eval_fg_device": (C.c_int, [_P, _P, _P, _P]),
+    "grape_b200_enqueue_forward": (C.c_int, [_P, _P]),
+    "grape_b200_enqueue_backward": (C.c_int, [_P]),
+    "grape_b200_enqueue_combine": (C.c_int, [_P]),
+    "grape_b200_finish": (C.c_int, [_P]),
     "grape_b200_device_ptr": (_P, [_P, C.c_int32]),
     "grape_b200_stream": (_P, [_P]),
     "grape_b200_launch_count": (C.c_int64, [_P]),

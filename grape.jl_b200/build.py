@@ -26,7 +26,23 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
+PEAKS_SRC = os.path.join(HERE, "csrc", "peaks.cu")
+PEAKS_OUT = os.path.join(HERE, "libgrape_peaks.so")
+
+
+def build_peaks(force=False):
+    if not force and os.path.exists(PEAKS_OUT) and os.path.getmtime(PEAKS_OUT) >= os.path.getmtime(PEAKS_SRC):
+        return PEAKS_OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    r = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", PEAKS_OUT, PEAKS_SRC], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libgrape_peaks.so")
+    return PEAKS_OUT
+
+
 def build(force=False, verbose=False):
+    build_peaks(force)
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")

@@ -561,6 +561,52 @@ int grape_b200_backward_chi(grape_b200_handle* h, const double* chiT, double* G_
     return backward_common(h, h->d_chi_host, G_partial, nullptr, J_b_partial, grad_J_a);
 }
 
+__global__ void __launch_bounds__(256) combine_grad(DevP p) {
+    // G = grad_J_Tb + lambda_a * grad_J_a   (after the caller all-reduced grad_J_Tb in place)
+    const int LNT = p.L * p.NT;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < LNT; idx += gridDim.x * blockDim.x)
+        p.grad[idx] = p.ja_kind ? fma(p.lambda_a, p.grad[2 * LNT + idx], p.grad[LNT + idx]) : p.grad[LNT + idx];
+}
+
+int grape_b200_enqueue_forward(grape_b200_handle* h, const double* d_pulsevals) {
+    if (!h || !d_pulsevals) return GRAPE_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->p.eps = d_pulsevals;
+    rec(h, 0);
+    CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
+    run_formU(h); rec(h, 1);
+    run_forward(h); rec(h, 2); rec(h, 3);
+    h->forward_done = true; h->backward_done = false;
+    return 0;
+}
+int grape_b200_enqueue_backward(grape_b200_handle* h) {
+    if (!h) return GRAPE_B200_EINVAL;
+    if (!h->forward_done) { h->err = "enqueue_backward before enqueue_forward"; return GRAPE_B200_ESTATE; }
+    if (h->p.functional == GRAPE_B200_JT_HOST) { h->err = "JT_HOST: use grape_b200_backward_chi"; return GRAPE_B200_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    run_backward(h, nullptr); rec(h, 4);
+    run_gradient(h);
+    run_finalize(h, true); rec(h, 5); rec(h, 6);
+    h->backward_done = true;
+    return 0;
+}
+int grape_b200_enqueue_combine(grape_b200_handle* h) {
+    if (!h) return GRAPE_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int blocks = (h->LNT + 255) / 256;
+    combine_grad<<<blocks < 296 ? blocks : 296, 256, 0, h->stream>>>(h->p);
+    h->launches++;
+    return 0;
+}
+int grape_b200_finish(grape_b200_handle* h) {
+    if (!h) return GRAPE_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_out + h->off_flags, h->p.flags, sizeof(DevFlags), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return check_flags(h);
+}
+
 int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, double* d_G, double* d_J_parts) {
     if (!h || !d_pulsevals) return GRAPE_B200_EINVAL;
     if (h->p.functional == GRAPE_B200_JT_HOST) { h->err = "eval_fg_device needs a built-in functional"; return GRAPE_B200_EINVAL; }

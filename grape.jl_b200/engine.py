@@ -182,6 +182,18 @@ class GrapeEngine:
     def eval_fg_device(self, d_pulsevals_ptr, d_G_ptr=None, d_J_ptr=None):
         self._check(self.lib.grape_b200_eval_fg_device(self._h, d_pulsevals_ptr, d_G_ptr, d_J_ptr))
 
+    def enqueue_forward(self, d_pulsevals_ptr):
+        self._check(self.lib.grape_b200_enqueue_forward(self._h, d_pulsevals_ptr))
+
+    def enqueue_backward(self):
+        self._check(self.lib.grape_b200_enqueue_backward(self._h))
+
+    def enqueue_combine(self):
+        self._check(self.lib.grape_b200_enqueue_combine(self._h))
+
+    def finish(self):
+        self._check(self.lib.grape_b200_finish(self._h))
+
     def device_ptr(self, which):
         return self.lib.grape_b200_device_ptr(self._h, which)
 

@@ -1,0 +1,121 @@
+"""Trajectory sharding over ranks (one process per GPU).
+
+The trajectory ensemble is split into contiguous blocks, one per rank
+(`GrapeProblem.shard`).  Per gradient evaluation there are exactly two tiny
+exchanges, the only points where trajectories couple (reference
+src/optimize.jl:755-760, 845-855 through the functional, and :574-584 through
+the sum over k):
+  1. all-reduce(sum) of the 4 partial sums (sum w tau, sum w|tau|^2, sum J_b)
+     after the forward sweep;
+  2. all-reduce(sum) of the partial gradient [L*NT] after the backward sweep.
+The host-side optimizer step is unchanged and identical on every rank."""
+from __future__ import annotations
+
+import numpy as np
+
+
+class ShardedGrape:
+    """Same `evaluate_gradient(G, x)` / `evaluate_functional(x)` surface as GrapeEngine,
+    for a problem sharded over `torch.distributed` ranks.
+
+    `engine_factory(local_problem) -> engine` builds the per-rank engine (the CUDA
+    GrapeEngine in production).  Collectives run on `device` tensors when given
+    (NCCL) or on CPU tensors (gloo)."""
+
+    def __init__(self, problem, engine_factory, rank=None, world=None, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.problem = problem
+        self.local = problem.shard(self.rank, self.world)
+        self.engine = engine_factory(self.local)
+        self.device = device
+        LNT = problem.L * problem.NT
+        kw = dict(dtype=torch.float64, device=device if device is not None else "cpu")
+        self._sums = torch.zeros(4, **kw)
+        self._grad = torch.zeros(LNT, **kw)
+        self._G_partial = np.zeros(LNT)
+        self.J_parts = np.zeros(3)
+        self.grad_J_Tb = np.zeros(LNT)
+        self.grad_J_a = np.zeros(LNT)
+        self.K_local = self.local.K
+
+    def _allreduce(self, buf, host):
+        t = self._torch
+        buf.copy_(t.from_numpy(host))
+        if self.world > 1:
+            self._dist.all_reduce(buf, op=self._dist.ReduceOp.SUM, group=self.group)
+        return buf.cpu().numpy()
+
+    def evaluate_gradient(self, G, pulsevals):
+        e = self.engine
+        sums = e.forward(pulsevals)
+        sums_g = self._allreduce(self._sums, sums)
+        self.J_parts[:] = e.backward(sums_g, self._G_partial)
+        self.grad_J_Tb[:] = self._allreduce(self._grad, self._G_partial)
+        self.grad_J_a[:] = e.grad_J_a
+        G[:] = self.grad_J_Tb
+        if self.problem.ja_kind:
+            G += self.problem.lambda_a * self.grad_J_a
+        return float(np.sum(self.J_parts))
+
+    def evaluate_functional(self, pulsevals):
+        # forward only; J_T from the reduced sums (same formulas as finalize_J)
+        p = self.problem
+        sums = self._allreduce(self._sums, self.engine.forward(pulsevals))
+        Kg = float(p.K_global)
+        if p.functional == 0:
+            JT = 1.0 - (sums[0] ** 2 + sums[1] ** 2) / Kg ** 2
+        elif p.functional == 1:
+            JT = 1.0 - sums[0] / Kg
+        else:
+            JT = 1.0 - sums[2] / Kg
+        self.J_parts[0] = JT
+        if p.ja_kind:
+            dt = np.diff(p.tlist)
+            e2 = np.asarray(pulsevals).reshape(p.L, p.NT) ** 2
+            self.J_parts[1] = p.lambda_a * float(np.sum(e2 * dt[None, :]))
+        self.J_parts[2] = p.lambda_b * sums[3] if p.gb_kind else 0.0
+        return float(np.sum(self.J_parts))
+
+
+class _DevArray:
+    """Raw device pointer -> object torch.as_tensor understands."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(int(ptr), False), version=2)
+
+
+class DevicePipeline:
+    """Device-resident gradient evaluation: pulse values already in HBM, both
+    exchanges done IN PLACE on the engine's device buffers by NCCL on the
+    engine's stream, no host synchronisation inside a step.
+
+    Call `step()` under `torch.cuda.stream(torch.cuda.ExternalStream(engine.stream()))`."""
+
+    def __init__(self, engine, dist=None, group=None):
+        import torch
+        self.engine, self.dist, self.group = engine, dist, group
+        LNT = engine.L * engine.NT
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.sums_t = torch.as_tensor(_DevArray(engine.device_ptr(1), 4), device=dev)
+        self.gTb_t = torch.as_tensor(_DevArray(engine.device_ptr(0), LNT), device=dev)
+        self.G_t = torch.as_tensor(_DevArray(engine.device_ptr(3), LNT), device=dev)
+
+    def step(self, d_eps):
+        e = self.engine
+        e.enqueue_forward(d_eps.data_ptr())
+        if self.dist is not None:
+            self.dist.all_reduce(self.sums_t, op=self.dist.ReduceOp.SUM, group=self.group)
+        e.enqueue_backward()
+        if self.dist is not None:
+            self.dist.all_reduce(self.gTb_t, op=self.dist.ReduceOp.SUM, group=self.group)
+            e.enqueue_combine()
+
+    def finish(self):
+        self.engine.finish()
+
+    def gradient(self):
+        return self.G_t

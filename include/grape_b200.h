@@ -172,9 +172,22 @@ int grape_b200_set_profiling(grape_b200_handle* h, int32_t on);
  * handle's own stream). */
 int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, double* d_G,
                               double* d_J_parts /* 3, device, may be NULL */);
+/* Asynchronous device pipeline (no host synchronisation, nothing copied): used when
+ * the two exchanges of a sharded evaluation are done in place on device buffers by
+ * the caller's collective library on the handle's stream:
+ *   enqueue_forward(d_pulsevals)  -> local sums at device_ptr(1)      [all-reduce in place]
+ *   enqueue_backward()            -> local grad_J_Tb at device_ptr(0) [all-reduce in place]
+ *   enqueue_combine()             -> G = grad_J_Tb + lambda_a*grad_J_a at device_ptr(3)
+ *   finish()                      -> synchronise, report chi-norm / Taylor errors
+ * With one shard, enqueue_forward + enqueue_backward + finish is a complete
+ * evaluate_gradient! (G at device_ptr(3)). */
+int grape_b200_enqueue_forward(grape_b200_handle* h, const double* d_pulsevals);
+int grape_b200_enqueue_backward(grape_b200_handle* h);
+int grape_b200_enqueue_combine(grape_b200_handle* h);
+int grape_b200_finish(grape_b200_handle* h);
 /* Device pointer of the handle's gradient buffer [L*NT] and sums buffer [4]
  * (for in-place collectives by the caller). */
-void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which); /* 0: grad partial, 1: sums, 2: pulsevals */
+void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which); /* 0: grad_J_Tb (local partial), 1: sums[4], 2: pulsevals, 3: G */
 /* cudaStream_t the handle launches on (so callers can time with events on it). */
 void* grape_b200_stream(grape_b200_handle* h);
 /* number of kernels launched by this handle since creation */

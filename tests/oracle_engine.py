@@ -1,0 +1,64 @@
+"""Oracle-backed stand-in for GrapeEngine (same method surface), so the host
+logic (optimize loop, sharding) can be tested on CPU. Test infrastructure only."""
+import numpy as np
+
+from oracle import grape_oracle as go
+
+
+class OracleEngine:
+    def __init__(self, problem, device=0):
+        self.problem = problem
+        self.op = go.from_problem(problem)
+        self.K, self.N, self.L, self.NT = problem.K, problem.N, problem.L, problem.NT
+        self.J_parts = np.zeros(3)
+        self.tau_vals = np.zeros(problem.K, dtype=np.complex128)
+        LNT = problem.L * problem.NT
+        self.grad_J_Tb, self.grad_J_a = np.zeros(LNT), np.zeros(LNT)
+        self.sums = np.zeros(4)
+        self._last = None
+
+    def evaluate_functional(self, x):
+        r = go.evaluate_functional(self.op, x)
+        self._last = r
+        self.J_parts[:] = r["J_parts"]
+        self.tau_vals[:] = r["tau"]
+        return r["J"]
+
+    def evaluate_gradient(self, G, x):
+        r = go.evaluate_gradient(self.op, x)
+        self._last = r
+        G[:] = r["G"]
+        self.J_parts[:] = r["J_parts"]
+        self.tau_vals[:] = r["tau"]
+        self.grad_J_Tb[:] = r["grad_J_Tb"]
+        self.grad_J_a[:] = r["grad_J_a"]
+        return r["J"]
+
+    def final_states(self):
+        return self._last["final_states"]
+
+    # split protocol: emulate with the oracle's sigma_reduce hook
+    def forward(self, x):
+        self._x = np.array(x, dtype=np.float64)
+        r = go.evaluate_functional(self.op, x, sigma_reduce=lambda v: v)
+        self._last = r
+        w = self.op.weights
+        self.tau_vals[:] = r["tau"]
+        s = np.sum(w * r["tau"])
+        self.sums[:] = [s.real, s.imag, np.sum(w * np.abs(r["tau"]) ** 2), np.sum(r["J_b_trajectory"])]
+        return self.sums.copy()
+
+    def backward(self, sums_global, G_partial):
+        sig = complex(sums_global[0], sums_global[1])
+
+        def red(v):
+            if np.ndim(v) == 0:      # scalar ingredient of the functional
+                return sig if self.op.functional in (go.SM, go.RE) else complex(sums_global[2], 0.0)
+            return v                 # gradient: stays a local partial
+        r = go.evaluate_gradient(self.op, self._x, sigma_reduce=red)
+        G_partial[:] = r["grad_J_Tb"]
+        self.grad_J_a[:] = r["grad_J_a"]
+        self.J_parts[:] = r["J_parts"]
+        if self.op.gb_kind:
+            self.J_parts[2] = self.op.lambda_b * sums_global[3]
+        return self.J_parts.copy()

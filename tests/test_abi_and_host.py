@@ -1,0 +1,109 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol the header
+declares; host-side logic (configs, sharding, import shim, C oracle)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import grape.jl_b200 as gb
+from grape.jl_b200 import configs, _lib
+from oracle import grape_oracle as go
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(lib_built):
+    hdr = open(os.path.join(ROOT, "include", "grape_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(grape_b200_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(lib_built)
+    for name in declared:
+        assert hasattr(lib, name), f"missing export {name}"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert _lib.load().grape_b200_abi_version() == 1
+
+
+def test_descriptor_struct_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "grape_b200.h")).read()
+    body = re.search(r"typedef struct grape_b200_problem \{(.*?)\} grape_b200_problem;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_0-9]+)\s*;", body)
+    assert names == [f[0] for f in _lib.ProblemDesc._fields_]
+
+
+def test_no_cpu_fallback_without_gpu(lib_built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from grape.jl_b200.engine import GrapeEngine, GrapeError
+    with pytest.raises(GrapeError, match="no CPU fallback"):
+        GrapeEngine(configs.c1_readme()[0])
+
+
+def test_create_argument_validation(lib_built):
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    d = _lib.ProblemDesc()
+    d.abi_version = 99
+    assert lib.grape_b200_create(ctypes.byref(d), ctypes.byref(h)) == 1
+    d.abi_version = 1
+    d.K, d.N, d.NT, d.G, d.L = 1, 2, 5, 1, 0
+    assert lib.grape_b200_create(ctypes.byref(d), ctypes.byref(h)) == 5   # ENOCONTROLS
+    assert b"no controls in trajectories" in lib.grape_b200_last_error(None)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "grape.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/", "").lower() or f == "sharded.py" or \
+                    not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_configs_shapes():
+    for name, (K, N, L, NT) in {"c1": (1, 2, 1, 500), "c2": (4, 6, 2, 2000)}.items():
+        p, eps = configs.CONFIGS[name]()
+        assert (p.K, p.N, p.L, p.NT) == (K, N, L, NT) and eps.shape == (L * NT,)
+    p, eps = configs.c3_ensemble(n_delta=4, n_amp=5, NT=10)
+    assert (p.K, p.G, p.N) == (20, 20, 3)
+    p, eps = configs.c4_dense450(N=12, K=3, NT=4)
+    assert np.allclose(p.tgt @ p.tgt.conj().T, np.eye(3))
+    assert np.max(np.abs(np.linalg.eigvalsh(p.H0[0]))) == pytest.approx(1.0)
+
+
+def test_shard_partition_covers_all_trajectories():
+    p, _ = configs.random_problem(K=11, N=3, L=2, NT=5, G=4, seed=3)
+    seen = []
+    for r in range(3):
+        s = p.shard(r, 3)
+        assert s.K_global == 11
+        for k in range(s.K):
+            g = s.gen_of_traj[k]
+            seen.append((s.psi0[k].tobytes(), s.H0[g].tobytes()))
+    full = [(p.psi0[k].tobytes(), p.H0[p.gen_of_traj[k]].tobytes()) for k in range(p.K)]
+    assert seen == full
+
+
+def test_c_oracle_matches_python_oracle():
+    from oracle import c_oracle as co
+    from scipy.linalg import expm
+    rng = np.random.default_rng(0)
+    for n, sc in [(3, 1e-3), (5, 0.1), (4, 0.5), (6, 1.5), (7, 4.0), (9, 30.0)]:
+        A = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))) * sc
+        E = expm(A)
+        assert np.max(np.abs(co.expm(A) - E)) < 1e-12 * np.max(np.abs(E))
+    D = np.diag([0.0, 1.0, 0.5]).astype(complex)
+    for fn in (gb.SM, gb.RE, gb.SS):
+        p, eps = configs.random_problem(K=4, N=3, L=2, NT=14, seed=5, functional=fn, gb_kind=1, gb_D=D,
+                                        lambda_b=0.4, ja_kind=1, lambda_a=0.3, shaped=True, hermitian=False,
+                                        G=2)
+        r = go.evaluate_gradient(go.from_problem(p), eps)
+        c = co.evaluate_gradient(p, eps)
+        assert np.max(np.abs(r["G"] - c["G"])) < 1e-12 * np.max(np.abs(r["G"]))
+        assert abs(r["J"] - c["J"]) < 1e-12
+        assert np.max(np.abs(r["tau"] - c["tau"])) < 1e-12

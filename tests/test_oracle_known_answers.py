@@ -1,0 +1,178 @@
+"""Pins the CPU oracle against every RNG-free known answer / identity the
+reference's own tests hold for the hot path, plus finite
+differences and the analytic Rabi formula.  CPU only."""
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+import grape.jl_b200 as gb
+from grape.jl_b200 import configs
+from grape.jl_b200.optimize import optimize, Trajectory, hamiltonian, J_T_sm, Control
+from oracle import grape_oracle as go
+from tests.oracle_engine import OracleEngine
+
+
+def test_c1_analytic_rabi_and_survey_numbers():
+    p, eps = configs.c1_readme()
+    r = go.evaluate_gradient(go.from_problem(p), eps)
+    om = np.sqrt(1 + 0.2 ** 2)
+    assert abs(r["J_parts"][0] - (1 - (0.2 ** 2 / om ** 2) * np.sin(om * 5) ** 2)) < 1e-13
+    assert abs(r["J"] - 0.9670069862873) < 1e-12
+    assert abs(np.linalg.norm(r["G"]) - 0.0530029505851244) < 1e-14
+    assert abs(r["G"][0] - 1.33673445010e-3) < 1e-13 and abs(r["G"][499] - 1.33673445010e-3) < 1e-13
+    assert abs(r["G"][250] - 3.545516018338e-3) < 1e-14
+
+
+@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
+def test_finite_differences(functional):
+    D = np.diag([0.0, 1.0, 0.5])
+    p, eps = configs.random_problem(K=2, N=3, L=2, NT=8, seed=1, functional=functional, shaped=True,
+                                    gb_kind=gb.GB_QUADFORM, gb_D=D, lambda_b=0.4,
+                                    ja_kind=gb.JA_FLUENCE, lambda_a=0.3, weights=np.array([0.7, 1.3]))
+    op = go.from_problem(p)
+    r = go.evaluate_gradient(op, eps)
+    fd = go.finite_difference_gradient(op, eps, range(len(eps)), h=1e-6)
+    assert np.max(np.abs(fd - r["G"])) < 1e-7 * max(1.0, np.max(np.abs(r["G"])))
+
+
+def test_taylor_equals_gradgen():
+    # reference test/test_tls_optimization.jl:204-233 (|dJ_T| < 1e-10) -- and element-wise
+    p, eps = configs.random_problem(K=2, N=4, L=3, NT=10, seed=2, hermitian=False)
+    a = go.evaluate_gradient(go.from_problem(p, gradient_method=go.GRADGEN), eps)
+    b = go.evaluate_gradient(go.from_problem(p, gradient_method=go.TAYLOR), eps)
+    assert abs(a["J"] - b["J"]) < 1e-10
+    assert np.max(np.abs(a["G"] - b["G"])) < 1e-13 * np.max(np.abs(a["G"]))
+
+
+def test_taylor_grad_step_vs_commutator_series():
+    """reference test/test_taylor_grad.jl:13-71: non-Hermitian 10x10, dt = +-1.25,
+    against U * sum_n -(i dt)^n/n! ad_H^{n-1}(mu), tolerance 1e-14."""
+    rng = np.random.default_rng(3991576559)
+    N = 10
+
+    def rmat():   # spectral radius ~1 random non-Hermitian matrix (random_matrix of QuantumControlTestUtils)
+        A = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+        return A / np.max(np.abs(np.linalg.eigvals(A)))
+
+    H = rmat() + rmat() + rmat()
+    psi = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    psi /= np.linalg.norm(psi)
+
+    def U_grad(H, mu, dt):
+        U = expm(-1j * H * dt)
+        Cm = mu
+        total = (-1j * dt) * Cm
+        fact, n = 1.0, 2
+        while True:
+            Cm = H @ Cm - Cm @ H
+            fact *= n
+            term = -((1j * dt) ** n / fact) * Cm
+            total = total + term
+            if np.linalg.norm(term) < 1e-16:
+                break
+            n += 1
+        return U @ total
+
+    for dt in (1.25, -1.25):
+        for mu in (rmat(), rmat()):
+            ref = U_grad(H, mu, dt) @ psi
+            got = go.taylor_grad_step(psi, H, mu, dt)
+            assert np.linalg.norm(ref - got) < 1e-13
+
+
+def test_taylor_grad_step_nonconvergence_message():
+    H = np.eye(3) * 50.0
+    with pytest.raises(RuntimeError, match="did not converge within 5 iterations"):
+        go.taylor_grad_step(np.ones(3, dtype=complex), H, H, 1.0, max_order=5)
+
+
+def test_J_b_bookkeeping():
+    # reference test/test_state_running_cost.jl:41-48: lambda_b * sum(J_b_trajectory) == J_parts[3]
+    D = np.diag([0.0, 1.0, 0.0])
+    p, eps = configs.random_problem(K=3, N=3, L=2, NT=9, seed=4, gb_kind=gb.GB_QUADFORM, gb_D=D, lambda_b=0.4)
+    op = go.from_problem(p)
+    r = go.evaluate_functional(op, eps)
+    assert abs(op.lambda_b * np.sum(r["J_b_trajectory"]) - r["J_parts"][2]) < 1e-15
+    # trapezoid rule recomputed from the stored states
+    tl, st = op.tlist, r["storage"]
+    w = np.zeros(op.NT + 1)
+    w[0], w[-1] = (tl[1] - tl[0]) / 2, (tl[-1] - tl[-2]) / 2
+    w[1:-1] = 0.5 * (tl[2:] - tl[:-2])
+    for k in range(3):
+        jb = sum(w[n] * np.real(np.vdot(st[k, :, n], D @ st[k, :, n])) for n in range(op.NT + 1))
+        assert abs(jb - r["J_b_trajectory"][k]) < 1e-13
+
+
+def test_chi_min_norm_guard():
+    p, eps = configs.c1_readme(NT=4)
+    p.H0[:] = 0
+    p.Hc[:] = 0
+    with pytest.raises(RuntimeError, match="chi_min_norm"):
+        go.evaluate_gradient(go.from_problem(p), eps)
+
+
+# ---- optimisation-level pins of the reference tests (host loop + oracle engine) ----
+def _tls_problem():
+    eps = lambda t: 0.2 * float(configs.flattop(np.array([t]), T=5.0, t_rise=0.3)[0])
+    H = hamiltonian(-0.5 * np.diag([1.0, -1.0]), ([[0, 1], [1, 0]], eps))
+    tlist = np.linspace(0, 5, 501)
+    traj = Trajectory([1, 0], H, target_state=[0, 1])
+    return [traj], tlist
+
+
+def test_tls_optimization_five_iterations():
+    # test/test_tls_optimization.jl:148-173: J_T < 1e-3 after 5 iterations, 0.75 < max|eps| < 0.85
+    trajs, tlist = _tls_problem()
+    res = optimize(trajs, tlist, J_T=J_T_sm, iter_stop=5, engine_factory=OracleEngine)
+    assert res.iter == 5 and res.converged
+    assert res.J_T < 1e-3
+    assert 0.75 < np.max(np.abs(res.optimized_controls[0])) < 0.85
+
+
+def test_tls_optimization_bounds():
+    # test/test_tls_optimization.jl:236-263: bounds +-0.7 -> 0.65 < max|eps| < 0.700001
+    trajs, tlist = _tls_problem()
+    res = optimize(trajs, tlist, J_T=J_T_sm, iter_stop=5, upper_bound=0.7, lower_bound=-0.7,
+                   engine_factory=OracleEngine)
+    assert 0.65 < np.max(np.abs(res.optimized_controls[0])) < 0.700001
+
+
+def test_tls_taylor_vs_gradgen():
+    # test/test_tls_optimization.jl:204-233
+    trajs, tlist = _tls_problem()
+    a = optimize(trajs, tlist, J_T=J_T_sm, iter_stop=5, engine_factory=OracleEngine)
+    trajs, tlist = _tls_problem()
+    b = optimize(trajs, tlist, J_T=J_T_sm, iter_stop=5, gradient_method="taylor", engine_factory=OracleEngine)
+    assert abs(a.J_T - b.J_T) < 1e-10
+
+
+def test_readme_example_converges():
+    # test/test_readme_example.jl:8-41: converged with J_T < 1e-3
+    H = hamiltonian([[1, 0], [0, -1]], ([[0, 1], [1, 0]], lambda t: 0.2))
+    tlist = np.linspace(0, 5, 501)
+    traj = Trajectory([1, 0], H, target_state=[0, 1])
+    res = optimize([traj], tlist, J_T=J_T_sm,
+                   check_convergence=lambda r: (r.J_T < 1e-3) and "J_T < 10⁻³",
+                   engine_factory=OracleEngine)
+    assert res.converged and res.J_T < 1e-3 and res.message == "J_T < 10⁻³"
+
+
+def test_continue_from():
+    # test/test_tls_optimization.jl:417-482: continuation reproduces J_T at iteration 0
+    trajs, tlist = _tls_problem()
+    a = optimize(trajs, tlist, J_T=J_T_sm, iter_stop=3, engine_factory=OracleEngine,
+                 callback=lambda wrk, i: (i, wrk.J_parts[0]))
+    trajs, tlist = _tls_problem()
+    b = optimize(trajs, tlist, J_T=J_T_sm, iter_stop=5, continue_from=a, engine_factory=OracleEngine,
+                 callback=lambda wrk, i: (i, wrk.J_parts[0]))
+    first_of_b = [r for r in b.records if r[0] == 0][-1]
+    assert abs(first_of_b[1] - 0.0) >= 0
+    assert abs(first_of_b[1] - [r for r in b.records if r[0] == 3][0][1]) < 1e-12
+
+
+def test_no_controls_error():
+    # test/test_empty_optimization.jl:36-37
+    traj = Trajectory([1, 0], hamiltonian(np.diag([1.0, -1.0])), target_state=[0, 1])
+    with pytest.raises(RuntimeError, match="no controls in trajectories: cannot optimize"):
+        optimize([traj], np.linspace(0, 1, 11), J_T=J_T_sm, engine_factory=OracleEngine,
+                 rethrow_exceptions=True)

@@ -392,7 +392,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     h->LNT = p.L * p.NT;
     h->path = choose_path(p.N, d->path);
     if (h->path == GRAPE_B200_PATH_SMALL && p.N > 4) { h->err = "PATH_SMALL requires N <= 4"; return bail(GRAPE_B200_EINVAL); }
-    if (h->path == GRAPE_B200_PATH_WARP && p.N > WARP_MAX_N) { h->err = "PATH_WARP requires N <= 64"; return bail(GRAPE_B200_EINVAL); }
+    if (h->path == GRAPE_B200_PATH_WARP && p.N > WARP_MAX_N) { h->err = "PATH_WARP requires N <= 32"; return bail(GRAPE_B200_EINVAL); }
 
     const int K = p.K, LNT = h->LNT;
     {

@@ -76,7 +76,7 @@ extern "C" {
 /* execution path selector (0 = choose from N) */
 #define GRAPE_B200_PATH_AUTO   0
 #define GRAPE_B200_PATH_SMALL  1  /* N <= 4: one thread per (trajectory, step), registers   */
-#define GRAPE_B200_PATH_WARP   2  /* N <= 64: sub-warp per (trajectory, step), shuffles     */
+#define GRAPE_B200_PATH_WARP   2  /* N <= 32: sub-warp per (trajectory, step), shuffles     */
 #define GRAPE_B200_PATH_DENSE  3  /* any N: polynomial apply on state blocks, DMMA ZGEMM    */
 
 /* Problem descriptor = the hot fields of GrapeWrk (src/workspace.jl:78-144). */

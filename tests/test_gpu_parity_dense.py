@@ -1,0 +1,77 @@
+"""GPU parity: dense DMMA path (N > 32, or forced) vs the CPU oracle, through the C-ABI."""
+import numpy as np
+import pytest
+
+import grape.jl_b200 as gb
+from grape.jl_b200 import configs
+from oracle import grape_oracle as go
+from tests.test_gpu_parity_small import check, engine
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,K", [(33, 3), (40, 8), (64, 5), (100, 16), (130, 9)])
+def test_dense_random(lib_built, N, K):
+    p, eps = configs.c4_dense450(N=N, K=K, NT=6)
+    check(p, eps)
+
+
+@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
+def test_dense_functionals_nonhermitian_shaped(lib_built, functional):
+    N, K = 36, 5
+    p, eps = configs.random_problem(K=K, N=N, L=3, NT=5, G=1, seed=70 + functional, hermitian=False, shaped=True,
+                                    weights=np.linspace(0.5, 1.5, K), functional=functional)
+    p.tlist = p.tlist * (0.5 / np.sqrt(N))
+    check(p, eps)
+
+
+def test_dense_forced_on_small_problem(lib_built):
+    p, eps = configs.random_problem(K=4, N=6, L=2, NT=8, G=1, seed=81, path=gb.PATH_DENSE)
+    p.tlist = p.tlist * 0.5
+    check(p, eps)
+
+
+def test_dense_large_norm_substeps(lib_built):
+    p, eps = configs.c4_dense450(N=48, K=4, NT=4)
+    p.tlist = p.tlist * 8.0      # ||H dt|| ~ 4: sub-steps
+    check(p, eps, rtol=1e-9)
+
+
+def test_dense_running_costs(lib_built):
+    p, eps = configs.c5_dense1024(N=40, K=6, NT=7)
+    e, ref = check(p, eps)
+    assert e.J_parts[1] > 0 and e.J_parts[2] > 0
+
+
+def test_dense_readbacks_and_split(lib_built):
+    p, eps = configs.c4_dense450(N=50, K=7, NT=5)
+    e, ref = check(p, eps)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    assert np.max(np.abs(e.final_states() - ref["final_states"])) < 1e-12
+    assert np.max(np.abs(e.stored_states(3) - ref["storage"][3])) < 1e-12
+    chi, rho = e.chi_states()
+    assert np.max(np.abs(chi - ref["chi_states"])) < 1e-12
+    sums = e.forward(eps)
+    Gp = np.zeros_like(eps)
+    e.backward(sums, Gp)
+    assert np.array_equal(Gp, G)
+
+
+def test_c4_reduced_steps_full_width(lib_built):
+    """C4 at full width (N=450, K=16) on 3 time steps: oracle parity."""
+    p, eps = configs.c4_dense450(NT=3)
+    check(p, eps)
+
+
+def test_c5_reduced_steps_full_width(lib_built):
+    """C5 at full width (N=1024, K=64, J_a + g_b) on 2 time steps: oracle parity on a
+    subset of the ensemble is too slow on CPU (N(L+1)=3072 expm), so compare against
+    the oracle's :taylor variant which needs only N x N exponentials."""
+    p, eps = configs.c5_dense1024(NT=2, K=8)
+    ref = go.evaluate_gradient(go.from_problem(p, gradient_method=go.TAYLOR), eps)
+    e = engine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    assert abs(J - ref["J"]) < 1e-10
+    assert np.max(np.abs(G - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))

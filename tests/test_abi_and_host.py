@@ -107,3 +107,27 @@ def test_c_oracle_matches_python_oracle():
         assert np.max(np.abs(r["G"] - c["G"])) < 1e-12 * np.max(np.abs(r["G"]))
         assert abs(r["J"] - c["J"]) < 1e-12
         assert np.max(np.abs(r["tau"] - c["tau"])) < 1e-12
+
+
+def test_julia_shim_matches_header():
+    """julia/GrapeB200.jl cannot run here (no Julia): check statically that its struct
+    mirrors `grape_b200_problem` field for field and that it only ccalls declared symbols."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "grape_b200.h")).read()
+    jl = open(os.path.join(root, "julia", "GrapeB200.jl")).read()
+    body = hdr[hdr.index("typedef struct grape_b200_problem {"):hdr.index("} grape_b200_problem;")]
+    c_fields = re.findall(r"^\s*(?:const\s+)?(int32_t|double)\s*(\*?)\s*(\w+)\s*;", body, flags=re.M)
+    sbody = jl[jl.index("struct Problem"):]
+    sbody = sbody[:sbody.index("\nend")]
+    j_fields = re.findall(r"^\s*(\w+)::([\w{}]+)\s*$", sbody, flags=re.M)
+    assert [f[2] for f in c_fields] == [f[0] for f in j_fields]
+    cmap = {("int32_t", ""): "Int32", ("double", ""): "Float64", ("int32_t", "*"): "Ptr{Int32}",
+            ("double", "*"): "Ptr{Float64}"}
+    for (ct, star, name), (jn, jt) in zip(c_fields, j_fields):
+        assert cmap[(ct, star)] == jt, (name, ct + star, jt)
+    from grape.jl_b200 import _lib
+    assert [f[0] for f in _lib.ProblemDesc._fields_] == [f[0] for f in j_fields]
+    for sym in re.findall(r"ccall\(\(:(\w+),", jl):
+        assert sym in _lib.SYMBOLS, sym

@@ -9,9 +9,11 @@
 #include "common.cuh"
 #include "reduce.cuh"
 #include "small_n.cuh"
+#include "small_seg.cuh"
 #include "warp_n.cuh"
 #include "dense.cuh"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,6 +46,9 @@ struct grape_b200_handle_impl {
     int64_t launches;
     WarpPlan warp;
     DensePlan dense;
+    bool seg_on;          // small path: time-segmented schedule (small_seg.cuh)
+    bool interior_done;   // small path, segmented: fw_storage filled inside the segments
+    SegArgs seg;
 };
 typedef grape_b200_handle_impl H;
 
@@ -76,6 +81,7 @@ int dev_upload(H* h, T** ptr, const T* src, size_t count) {
 }
 
 int choose_path(int N, int requested) {
+    if (requested == GRAPE_B200_PATH_SMALL_CHAIN) return GRAPE_B200_PATH_SMALL;
     if (requested != GRAPE_B200_PATH_AUTO) return requested;
     if (N <= 4) return GRAPE_B200_PATH_SMALL;
     if (N <= WARP_MAX_N) return GRAPE_B200_PATH_WARP;
@@ -150,10 +156,26 @@ int small_setup(H* h, const grape_b200_problem* d) {
     }
     if (int rc = dev_alloc(h, &p.U, (size_t)NT * NN * G)) return rc;
     if (int rc = dev_alloc(h, &p.psi, (size_t)(NT + 1) * N * K)) return rc;
-    if (int rc = dev_alloc(h, &p.chi, (size_t)(NT + 1) * N * K)) return rc;
+    if (d->gb_kind != 0 || d->path == GRAPE_B200_PATH_SMALL_CHAIN)
+        if (int rc = dev_alloc(h, &p.chi, (size_t)(NT + 1) * N * K)) return rc;
     int BK = 1;
     while (BK < K && BK < 128) BK <<= 1;
     p.KB = (K + BK - 1) / BK;
+    // time-segmented schedule unless a state running cost couples chi to the stored states at
+    // every step (optimize.jl:897-908) or the caller forces the plain chains
+    h->seg_on = (p.gb_kind == 0) && (d->path != GRAPE_B200_PATH_SMALL_CHAIN);
+    if (h->seg_on) {
+        SegArgs& a = h->seg;
+        int S = (int)std::ceil(std::sqrt((double)NT));
+        if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
+        a.S = S < 2 ? 2 : (S > 64 ? 64 : S);
+        a.NSEG = (NT + a.S - 1) / a.S;
+        a.BKL = 1;
+        while (a.BKL < K && a.BKL < 32) a.BKL <<= 1;
+        p.KB = (K + a.BKL - 1) / a.BKL;
+        if (int rc = dev_alloc(h, &a.Pseg, (size_t)a.NSEG * NN * G)) return rc;
+        if (int rc = dev_alloc(h, &a.chiE, (size_t)a.NSEG * N * K)) return rc;
+    }
     if (int rc = dev_alloc(h, &p.partial, (size_t)p.KB * L * NT)) return rc;
     switch (N) {
         case 1: return small_set_attrs<1>(h);
@@ -200,6 +222,52 @@ void small_gradient_t(H* h) {
     }
 }
 
+// ---- time-segmented schedule (small_seg.cuh)
+template <int N>
+void seg_prod_t(H* h) {
+    const long long tot = (long long)h->p.G * h->seg.NSEG;
+    small_segprod<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+    h->launches++;
+}
+template <int N>
+void seg_formseg_t(H* h) {
+    const long long tot = (long long)h->p.G * h->seg.NSEG;
+    small_formseg<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+    h->launches++;
+}
+template <int N>
+void seg_chain_fwd_t(H* h) {
+    small_segchain_fwd<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg);
+    h->launches++;
+}
+template <int N>
+void seg_fwd_t(H* h) {
+    const long long tot = (long long)h->p.K * h->seg.NSEG;
+    small_segfwd<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+    h->launches++;
+}
+template <int N>
+void seg_chain_bwd_t(H* h, const cplx* chi_host) {
+    small_segchain_bwd<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg, chi_host);
+    h->launches++;
+}
+template <int N, int LCMAX>
+void seg_grad_t(H* h) {
+    const DevP& p = h->p;
+    const SegArgs& a = h->seg;
+    const int SPW = 32 / a.BKL;
+    const long long warps = (long long)((p.K + a.BKL - 1) / a.BKL) * ((a.NSEG + SPW - 1) / SPW);
+    const unsigned blocks = (unsigned)((warps + 3) / 4);
+    int l0 = 0;
+    while (l0 < p.L) {
+        const int rem = p.L - l0;
+        if (LCMAX >= 4 && rem >= 4) { small_seggrad<N, (LCMAX >= 4 ? 4 : 1)><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 4; }
+        else if (LCMAX >= 2 && rem >= 2) { small_seggrad<N, (LCMAX >= 2 ? 2 : 1)><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 2; }
+        else { small_seggrad<N, 1><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 1; }
+        h->launches++;
+    }
+}
+
 #define SMALL_DISPATCH(N_, CALL1, CALL2, CALL3, CALL4) \
     switch (N_) { case 1: CALL1; break; case 2: CALL2; break; case 3: CALL3; break; default: CALL4; break; }
 
@@ -207,15 +275,33 @@ void small_gradient_t(H* h) {
 void run_formU(H* h) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
+            if (h->seg_on && (long long)h->p.G * h->seg.NSEG >= 32768 && !getenv("GRAPE_B200_NO_FORMSEG")) {
+                // enough (generator, segment) pairs to fill the GPU: fused formation + segment product
+                SMALL_DISPATCH(h->p.N, seg_formseg_t<1>(h), seg_formseg_t<2>(h), seg_formseg_t<3>(h), seg_formseg_t<4>(h));
+                break;
+            }
             SMALL_DISPATCH(h->p.N, small_formU_t<1>(h), small_formU_t<2>(h), small_formU_t<3>(h), small_formU_t<4>(h));
+            if (h->seg_on) { SMALL_DISPATCH(h->p.N, seg_prod_t<1>(h), seg_prod_t<2>(h), seg_prod_t<3>(h), seg_prod_t<4>(h)); }
             break;
         case GRAPE_B200_PATH_WARP: warp_run_formU(h->warp, h->p, h->stream, h->launches); break;
         case GRAPE_B200_PATH_DENSE: break;   // dense path never forms U
     }
 }
-void run_forward(H* h) {
+void run_fill_interior(H* h) {
+    if (h->path == GRAPE_B200_PATH_SMALL && h->seg_on && !h->interior_done) {
+        SMALL_DISPATCH(h->p.N, seg_fwd_t<1>(h), seg_fwd_t<2>(h), seg_fwd_t<3>(h), seg_fwd_t<4>(h));
+        h->interior_done = true;
+    }
+}
+void run_forward(H* h, bool need_storage = true) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
+            if (h->seg_on) {
+                SMALL_DISPATCH(h->p.N, seg_chain_fwd_t<1>(h), seg_chain_fwd_t<2>(h), seg_chain_fwd_t<3>(h), seg_chain_fwd_t<4>(h));
+                h->interior_done = false;
+                if (need_storage) run_fill_interior(h);
+                break;
+            }
             SMALL_DISPATCH(h->p.N, small_forward_t<1>(h), small_forward_t<2>(h), small_forward_t<3>(h), small_forward_t<4>(h));
             break;
         case GRAPE_B200_PATH_WARP: warp_run_forward(h->warp, h->p, h->stream, h->launches); break;
@@ -227,6 +313,12 @@ void run_forward(H* h) {
 void run_backward(H* h, const cplx* chi_host) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
+            if (h->seg_on) {
+                run_fill_interior(h);
+                SMALL_DISPATCH(h->p.N, seg_chain_bwd_t<1>(h, chi_host), seg_chain_bwd_t<2>(h, chi_host),
+                               seg_chain_bwd_t<3>(h, chi_host), seg_chain_bwd_t<4>(h, chi_host));
+                break;
+            }
             SMALL_DISPATCH(h->p.N, small_backward_t<1>(h, chi_host), small_backward_t<2>(h, chi_host),
                            small_backward_t<3>(h, chi_host), small_backward_t<4>(h, chi_host));
             break;
@@ -237,6 +329,10 @@ void run_backward(H* h, const cplx* chi_host) {
 void run_gradient(H* h) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
+            if (h->seg_on) {
+                SMALL_DISPATCH(h->p.N, (seg_grad_t<1, 4>(h)), (seg_grad_t<2, 4>(h)), (seg_grad_t<3, 2>(h)), (seg_grad_t<4, 1>(h)));
+                break;
+            }
             SMALL_DISPATCH(h->p.N, (small_gradient_t<1, 4>(h)), (small_gradient_t<2, 4>(h)),
                            (small_gradient_t<3, 2>(h)), (small_gradient_t<4, 1>(h)));
             break;
@@ -367,6 +463,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     h->d_tmp = nullptr; h->tmp_elems = 0; h->stream = nullptr;
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->launches = 0;
+    h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
     h->device = d->device;
     auto bail = [&](int rc) {
         g_create_error = h->err;
@@ -467,7 +564,7 @@ int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals, double* J_p
     rec(h, 0);
     if (int rc = upload_pulses(h, pulsevals)) return rc;
     run_formU(h); rec(h, 1);
-    run_forward(h); rec(h, 2);
+    run_forward(h, false); rec(h, 2);   // interior of fw_storage is filled lazily (get_stored_states)
     run_finalize(h, false); rec(h, 3); rec(h, 4); rec(h, 5);
     if (int rc = download_all(h)) return rc;
     collect_timings(h, l0);
@@ -681,6 +778,7 @@ int grape_b200_get_stored_states(grape_b200_handle* h, int32_t k, double* out) {
     const DevP& p = h->p;
     const size_t cnt = (size_t)(p.NT + 1) * p.N;
     if (int rc = ensure_tmp(h, cnt)) return rc;
+    run_fill_interior(h);
     if (h->path == GRAPE_B200_PATH_SMALL) {
         gather_small_states<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(p.psi, h->d_tmp, p.K, p.N, p.NT, k);
         h->launches++;

@@ -76,9 +76,10 @@ GB_HD void exp_plan(double nrm, int& degree, int& s) {
 GB_HD void vec_plan(double nrm, int& m, int& s) {
     s = 0;
     while (nrm > 1.0 && s < 30) { nrm *= 0.5; ++s; }
-    double t = 1.0;
-    m = 0;
-    do { ++m; t *= nrm / m; } while (t > 2e-17 && m < 40);
+    // theta^m/m! <= 2e-17  <=>  theta^m <= 2e-17 * m!   (no divisions: this runs once per unit)
+    double t = nrm, f = 1.0;
+    m = 1;
+    while (t > 2e-17 * f && m < 40) { ++m; t *= nrm; f *= (double)m; }
     if (m < 2) m = 2;
 }
 

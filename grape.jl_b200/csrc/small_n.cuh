@@ -420,6 +420,9 @@ __global__ void __launch_bounds__(128) small_gradient(DevP p, int l0, int BK) {
     const bool taylor = p.grad_method != 0;
     bool converged = !taylor || !p.taylor_check;
     double rlast = 0.0;
+    bool done[LC];   // per-control early return of taylor_grad_step! (optimize.jl:633-638)
+#pragma unroll
+    for (int l = 0; l < LC; ++l) done[l] = false;
     for (int sub = 0; sub < (1 << s); ++sub) {
         cplx ta[N], tb[LC][N];
 #pragma unroll
@@ -430,7 +433,6 @@ __global__ void __launch_bounds__(128) small_gradient(DevP p, int l0, int BK) {
             for (int i = 0; i < N; ++i) tb[l][i] = bsum[l][i];
         for (int j = 1; j <= m; ++j) {
             const double inv = 1.0 / (double)j;
-            double r2max = 0.0;
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 cplx nb[N];
@@ -448,9 +450,13 @@ __global__ void __launch_bounds__(128) small_gradient(DevP p, int l0, int BK) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) {
                     tb[l][i] = nb[i];
-                    bsum[l][i] = cadd(bsum[l][i], nb[i]);
+                    if (!done[l]) bsum[l][i] = cadd(bsum[l][i], nb[i]);
                 }
-                r2max = fmax(r2max, r2);
+                if (taylor && p.taylor_check && j >= 2 && !done[l]) {
+                    const double r = sqrt(r2);
+                    rlast = r;
+                    if (r < p.taylor_tol) done[l] = true;
+                }
             }
             {
                 cplx na[N];
@@ -467,9 +473,15 @@ __global__ void __launch_bounds__(128) small_gradient(DevP p, int l0, int BK) {
                     asum[i] = cadd(asum[i], na[i]);
                 }
             }
-            if (taylor && p.taylor_check && j >= 2) {   // optimize.jl:633-638
-                rlast = sqrt(r2max);
-                if (rlast < p.taylor_tol) { converged = true; break; }
+            if (taylor && p.taylor_check && j >= 2) {
+
+                bool all_done = true;
+#pragma unroll
+
+                for (int l = 0; l < LC; ++l) all_done = all_done && done[l];
+
+                if (all_done) { converged = true; break; }
+
             }
         }
     }

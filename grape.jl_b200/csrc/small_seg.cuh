@@ -1,0 +1,601 @@
+// small_seg.cuh -- time-segmented ("scan") schedule of the N <= 4 path.
+//
+// The time axis is strictly sequential (reference src/optimize.jl:731, 880), but a
+// chain of NT dependent 3x3 mat-vecs per trajectory is pure latency on a GPU.  The
+// propagators U_n only depend on eps_n, so the chain is cut into NSEG segments of S
+// steps:
+//   A1 small_form_U      (small_n.cuh)  all U_{g,n} in parallel
+//   A2 small_segprod     P_{g,seg} = U_{n1-1} ... U_{n0}          parallel over (g, seg)
+//   B1 small_segchain_fwd   Psi_k at the segment boundaries, tau_k  chain of NSEG steps
+//   B2 small_segchain_bwd   chi_k(T) boundary condition (optimize.jl:845-869) and chi_k at
+//                           the segment ends                        chain of NSEG steps
+//   C1 small_segfwd      fills fw_storage inside every segment      parallel over (k, seg)
+//   C2 small_seggrad     per (k, seg): walks the segment backwards carrying chi in
+//                        registers; per step the GradGenerator contraction
+//                        tau_grad[k][n,l] = rho_k <chi'_l | Psi_k(t_{n-1})>  (optimize.jl:893-895)
+//                        and chi <- exp(+i H^dagger dt) chi come from the same Krylov vectors.
+//
+// Contraction used by C2 when the step needs at most SEG_MMAX Taylor orders and no
+// sub-stepping (the usual piecewise-constant-control regime ||H dt|| << 1):
+//   <chi'_l|Psi> = Tr(E_l^dagger M),  M = sum_{a,b} beta(a,b) bh_a ch_b^dagger,
+//   bh_a = (-i H dt)^a Psi / a!,  ch_b = (+i H^dagger dt)^b chi / b!,  beta(a,b) = a! b!/(a+b+1)!
+// i.e. the Frechet derivative of the exponential (docs/src/background.md:447-494) written with
+// two Krylov sequences instead of the (1+2L) mat-vecs per order of the block recursion; the cost
+// is independent of the number of controls up to the final traces.  Otherwise C2 falls back to
+// the block recursion of small_gradient (small_n.cuh), which also serves gradient_method=:taylor.
+#pragma once
+#include "common.cuh"
+#include "small_n.cuh"
+
+constexpr int SEG_MMAX = 8;
+
+// beta(a,b) = a! b! / (a+b+1)!
+struct BetaTable {
+    double v[SEG_MMAX][SEG_MMAX];
+    constexpr BetaTable() : v() {
+        for (int a = 0; a < SEG_MMAX; ++a)
+            for (int b = 0; b < SEG_MMAX; ++b) {
+                // a! b!/(a+b+1)! = 1/((a+b+1) * C(a+b, a))
+                double c = 1.0;
+                for (int t = 1; t <= a; ++t) c = c * (double)(b + t) / (double)t;
+                v[a][b] = 1.0 / ((double)(a + b + 1) * c);
+            }
+    }
+};
+__constant__ BetaTable c_beta = BetaTable();
+
+struct SegArgs {
+    int S, NSEG;
+    cplx* Pseg;   // [NSEG][NN][G]
+    cplx* chiE;   // [NSEG][N][K]   chi_k at the END time point of each segment
+    int BKL;      // lanes of a warp that enumerate trajectories (power of two <= 32)
+};
+
+// ---------------------------------------------------------------------------
+// A2: segment propagators
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) small_segprod(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int G = p.G, NT = p.NT;
+    if (idx >= (long long)G * a.NSEG) return;
+    const int g = (int)(idx % G), seg = (int)(idx / G);
+    const int n0 = seg * a.S, n1 = min(NT, n0 + a.S);
+    cplx P[NN], Un[NN];
+    const cplx* Ug = p.U + g;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) P[c] = ld_cs(&Ug[((size_t)n0 * NN + c) * G]);
+    if (n0 + 1 < n1) {
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Un[c] = ld_cs(&Ug[((size_t)(n0 + 1) * NN + c) * G]);
+    }
+    for (int n = n0 + 1; n < n1; ++n) {
+        cplx Uc[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Uc[c] = Un[c];
+        if (n + 1 < n1) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Un[c] = ld_cs(&Ug[((size_t)(n + 1) * NN + c) * G]);
+        }
+        cplx T[NN];
+        sm_mm<N>(T, Uc, P);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) P[c] = T[c];
+    }
+    cplx* o = a.Pseg + (size_t)seg * NN * G + g;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) o[(size_t)c * G] = P[c];
+}
+
+// A1+A2 fused: thread per (g, seg) forms the S propagators of its segment one after the
+// other (stored for C1) and accumulates their product, so U is not re-read from HBM.
+// Used when G * NSEG alone fills the GPU; otherwise A1 (parallel over all (g, n)) + A2.
+template <int N>
+__global__ void __launch_bounds__(128) small_formseg(DevP p, SegArgs a) {
+    constexpr int NN = N * N, BS = SmallCfg<N>::BS;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int G = p.G, NT = p.NT;
+    if (idx >= (long long)G * a.NSEG) return;
+    const int g = (int)(idx % G), seg = (int)(idx / G);
+    const int n0 = seg * a.S, n1 = min(NT, n0 + a.S);
+    cplx Pacc[NN];
+    for (int n = n0; n < n1; ++n) {
+        const double dt = p.tlist[n + 1] - p.tlist[n];
+        cplx P[BS][NN];
+        cplx X[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) X[c] = __ldg(&p.H0[(size_t)c * G + g]);
+        for (int l = 0; l < p.L; ++l) {
+            double am = p.eps[l * NT + n];
+            if (p.shape) am *= p.shape[l * NT + n];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) cfmar(X[c], am, __ldg(&p.Hc[((size_t)l * NN + c) * G + g]));
+        }
+#pragma unroll
+        for (int c = 0; c < NN; ++c) P[0][c] = mk(dt * X[c].y, -dt * X[c].x);   // -i dt H
+        int degree, s;
+        exp_plan(sm_norm1<N>(P[0]), degree, s);
+        if (s > 0) {
+            const double sc = ldexp(1.0, -s);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) P[0][c] = cscale(P[0][c], sc);
+        }
+        sm_expm<N, BS>(P, X, degree, s);
+        cplx* Uo = p.U + (size_t)n * NN * G + g;
+#pragma unroll
+        for (int c = 0; c < NN; ++c) st_cs(&Uo[(size_t)c * G], X[c]);
+        if (n == n0) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Pacc[c] = X[c];
+        } else {
+            sm_mm<N>(P[0], X, Pacc);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Pacc[c] = P[0][c];
+        }
+    }
+    cplx* o = a.Pseg + (size_t)seg * NN * G + g;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) o[(size_t)c * G] = Pacc[c];
+}
+
+// ---------------------------------------------------------------------------
+// B1: forward chain over segment boundaries
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(64) small_segchain_fwd(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    const int K = p.K, G = p.G, NT = p.NT;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int g = p.gen[k];
+    const cplx* Pg = a.Pseg + g;
+    cplx psi[N], Pn[NN];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        psi[i] = p.psi0[(size_t)i * K + k];
+        st_cs(&p.psi[(size_t)i * K + k], psi[i]);
+    }
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[(size_t)c * G]);
+    for (int seg = 0; seg < a.NSEG; ++seg) {
+        cplx Pc[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Pc[c] = Pn[c];
+        if (seg + 1 < a.NSEG) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[((size_t)(seg + 1) * NN + c) * G]);
+        }
+        cplx nw[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) cfma(acc, Pc[i * N + j], psi[j]);
+            nw[i] = acc;
+        }
+        const int nb = min(NT, (seg + 1) * a.S);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            psi[i] = nw[i];
+            st_cs(&p.psi[((size_t)nb * N + i) * K + k], psi[i]);
+        }
+    }
+    cplx acc = mk(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) cfmac(acc, p.tgt[(size_t)i * K + k], psi[i]);
+    p.tau[k] = acc;
+    p.jb[k] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// B2: chi boundary condition + backward chain over segment boundaries
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(64) small_segchain_bwd(DevP p, SegArgs a, const cplx* __restrict__ chi_host) {
+    constexpr int NN = N * N;
+    const int K = p.K, G = p.G;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int g = p.gen[k];
+    const cplx* Pg = a.Pseg + g;
+    cplx Pn[NN];
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[((size_t)(a.NSEG - 1) * NN + c) * G]);
+    cplx x[N];
+    if (chi_host) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = chi_host[(size_t)k * N + i];
+    } else {   // optimize.jl:845-855 with the analytic chi of J_T_sm / J_T_re / J_T_ss
+        const double w = p.w ? p.w[k] : 1.0;
+        const double Kg = (double)p.Kglobal;
+        cplx c;
+        if (p.functional == 0) c = mk(w * p.sums[0] / (Kg * Kg), w * p.sums[1] / (Kg * Kg));
+        else if (p.functional == 1) c = mk(w / (2.0 * Kg), 0.0);
+        else { cplx t = p.tau[k]; c = mk(w * t.x / Kg, w * t.y / Kg); }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = cmul(c, p.tgt[(size_t)i * K + k]);
+    }
+    double rho = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) rho += cnorm2(x[i]);
+    rho = sqrt(rho);
+    if (!(rho >= p.chi_min_norm)) {   // optimize.jl:1021-1025
+        if (atomicCAS(&p.flags->chi_bad_k, 0, k + 1) == 0) p.flags->chi_bad_rho = rho;
+        rho = 1.0;
+    }
+    const double ir = 1.0 / rho;
+    p.rho[k] = rho;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        x[i] = cscale(x[i], ir);
+        p.chiT[(size_t)k * N + i] = x[i];
+    }
+    for (int seg = a.NSEG - 1; seg >= 0; --seg) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.chiE[((size_t)seg * N + i) * K + k] = x[i];
+        if (seg == 0) break;
+        cplx Pc[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Pc[c] = Pn[c];
+        if (seg - 1 > 0) {   // P of segment 0 is never needed
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[((size_t)(seg - 1) * NN + c) * G]);
+        }
+        cplx nw[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) cfmac(acc, Pc[j * N + i], x[j]);   // (P^dagger x)_i
+            nw[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = nw[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// C1: forward states inside every segment (thread per (k, seg), k fastest)
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) small_segfwd(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    const int K = p.K, G = p.G, NT = p.NT;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)K * a.NSEG) return;
+    const int k = (int)(idx % K), seg = (int)(idx / K);
+    const int n0 = seg * a.S, n1 = min(NT, n0 + a.S);
+    if (n0 + 1 >= n1) return;   // single-step segment: both ends come from the chain
+    const int g = p.gen[k];
+    const cplx* Ug = p.U + g;
+    cplx psi[N], Un[NN];
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Un[c] = ld_cs(&Ug[((size_t)n0 * NN + c) * G]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) psi[i] = p.psi[((size_t)n0 * N + i) * K + k];
+    for (int n = n0; n < n1 - 1; ++n) {   // the state at n1 was written by the chain
+        cplx Uc[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Uc[c] = Un[c];
+        if (n + 1 < n1 - 1) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Un[c] = ld_cs(&Ug[((size_t)(n + 1) * NN + c) * G]);
+        }
+        cplx nw[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) cfma(acc, Uc[i * N + j], psi[j]);
+            nw[i] = acc;
+        }
+        cplx* o = p.psi + ((size_t)(n + 1) * N) * K + k;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            psi[i] = nw[i];
+            st_cs(o + (size_t)i * K, psi[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// C2: backward walk through a segment fused with the gradient contraction
+// ---------------------------------------------------------------------------
+// one step, Krylov form. A = +i dt H^dagger (row-major). On exit chi <- exp(A) chi and
+// M = sum beta(a,b) bh_a ch_b^dagger.
+template <int N>
+GB_D void seg_step_krylov(const cplx (&A)[N * N], const cplx (&psi)[N], cplx (&chi)[N], cplx (&M)[N * N], int m) {
+    cplx e[SEG_MMAX][N];
+    cplx bv[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) bv[i] = psi[i];
+#pragma unroll
+    for (int b = 0; b < SEG_MMAX; ++b)
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[b][i] = cscale(bv[i], c_beta.v[0][b]);
+#pragma unroll
+    for (int aa = 1; aa < SEG_MMAX; ++aa) {
+        if (aa < m) {
+            // bv <- (A^dagger bv)/aa   (A^dagger = -i dt H)
+            cplx nb[N];
+            const double inv = 1.0 / (double)aa;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < N; ++q) cfmac(acc, A[q * N + i], bv[q]);
+                nb[i] = cscale(acc, inv);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) bv[i] = nb[i];
+#pragma unroll
+            for (int b = 0; b < SEG_MMAX - aa; ++b)
+#pragma unroll
+                for (int i = 0; i < N; ++i) cfmar(e[b][i], c_beta.v[aa][b], bv[i]);
+        }
+    }
+    cplx cv[N], acc_chi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { cv[i] = chi[i]; acc_chi[i] = chi[i]; }
+#pragma unroll
+    for (int c = 0; c < N * N; ++c) M[c] = mk(0.0, 0.0);
+#pragma unroll
+    for (int b = 0; b < SEG_MMAX; ++b) {
+        if (b < m) {
+#pragma unroll
+            for (int pp = 0; pp < N; ++pp)
+#pragma unroll
+                for (int q = 0; q < N; ++q) {   // M_pq += e_b[p] * conj(cv[q])
+                    cplx& t = M[pp * N + q];
+                    const cplx x = e[b][pp], y = cv[q];
+                    t.x = fma(x.x, y.x, t.x); t.x = fma(x.y, y.y, t.x);
+                    t.y = fma(x.y, y.x, t.y); t.y = fma(-x.x, y.y, t.y);
+                }
+            cplx nc[N];
+            const double inv = 1.0 / (double)(b + 1);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], cv[q]);
+                nc[i] = cscale(acc, inv);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { cv[i] = nc[i]; acc_chi[i] = cadd(acc_chi[i], nc[i]); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) chi[i] = acc_chi[i];
+}
+
+template <int N, int LC>
+__global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) {
+    constexpr int NN = N * N;
+    const int K = p.K, G = p.G, NT = p.NT;
+    const int lane = threadIdx.x & 31;
+    const int BKL = a.BKL, SPW = 32 / BKL;                 // segments per warp
+    const int KGR = (K + BKL - 1) / BKL;                   // trajectory groups
+    const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int SGR = (a.NSEG + SPW - 1) / SPW;              // segment groups
+    if (wid >= (long long)KGR * SGR) return;               // whole warp exits
+    const int kg = (int)(wid % KGR), sg = (int)(wid / KGR);
+    const int tk = lane % BKL, ts = lane / BKL;
+    const int k = kg * BKL + tk, seg = sg * SPW + ts;
+    const bool live = (k < K) && (seg < a.NSEG);
+    const int kk = k < K ? k : K - 1;
+    const int sseg = seg < a.NSEG ? seg : a.NSEG - 1;
+    const int n0 = sseg * a.S, n1 = min(NT, n0 + a.S);
+    const int g = p.gen[kk];
+    const double rho = p.rho[kk];
+    const bool taylor = p.grad_method != 0;
+
+    cplx chi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) chi[i] = a.chiE[((size_t)sseg * N + i) * K + kk];
+    cplx psin[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) psin[i] = ld_cs(&p.psi[((size_t)(n1 - 1) * N + i) * K + kk]);
+
+    for (int st = 0; st < a.S; ++st) {                     // uniform trip count across the warp
+        const int n = n1 - 1 - st;
+        const bool act = live && n >= n0;
+        const int nn = n >= n0 ? n : n0;
+        cplx psi[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) psi[i] = psin[i];
+        if (nn - 1 >= n0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) psin[i] = ld_cs(&p.psi[((size_t)(nn - 1) * N + i) * K + kk]);
+        }
+        const double dt = p.tlist[nn + 1] - p.tlist[nn];
+        // A = H^dagger (then scaled to +i dt H^dagger)
+        cplx A[NN];
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) A[i * N + j] = __ldg(&p.H0[(size_t)(j * N + i) * G + g]);
+        for (int l = 0; l < p.L; ++l) {
+            double am = p.eps[l * NT + nn];
+            if (p.shape) am *= p.shape[l * NT + nn];
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    cfmar(A[i * N + j], am, __ldg(&p.Hc[((size_t)l * NN + j * N + i) * G + g]));
+        }
+        int m, s;
+        {
+            const double nrm = dt * sm_norm1<N>(A);
+            if (!taylor) vec_plan(nrm, m, s);
+            else { s = 0; m = p.taylor_max_order; }
+        }
+        const double sc = dt * ldexp(1.0, -s);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) A[c] = mk(sc * A[c].y, sc * A[c].x);   // i*sc*conj(H_ji): A held H transposed
+        double red[LC];
+        cplx tg[LC];
+        // N = 4 does not fit the Krylov form in registers: block recursion only
+        const bool fast = (N <= 3) && __all_sync(0xffffffffu, !taylor && s == 0 && m <= SEG_MMAX);
+        if (N <= 3 && fast) {
+            cplx M[NN];
+            seg_step_krylov<N>(A, psi, chi, M, m);
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                double sl = sc;
+                if (p.shape) sl *= p.shape[(l0 + l) * NT + nn];
+                // E_pq = i*sl*conj(Hc[q][p]);  Tr(E^dagger M) = sum conj(E_pq) M_pq
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int pp = 0; pp < N; ++pp)
+#pragma unroll
+                    for (int q = 0; q < N; ++q) {
+                        const cplx h = __ldg(&p.Hc[((size_t)(l0 + l) * NN + q * N + pp) * G + g]);
+                        cfmac(acc, mk(sl * h.y, sl * h.x), M[pp * N + q]);
+                    }
+                tg[l] = cscale(acc, rho);
+            }
+        } else {
+            // block (GradGenerator) recursion, identical to small_gradient (small_n.cuh)
+            cplx E[LC][NN];
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                double sl = sc;
+                if (p.shape) sl *= p.shape[(l0 + l) * NT + nn];
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const cplx h = __ldg(&p.Hc[((size_t)(l0 + l) * NN + j * N + i) * G + g]);
+                        E[l][i * N + j] = mk(sl * h.y, sl * h.x);
+                    }
+            }
+            cplx asum[N], bsum[LC][N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) asum[i] = chi[i];
+#pragma unroll
+            for (int l = 0; l < LC; ++l)
+#pragma unroll
+                for (int i = 0; i < N; ++i) bsum[l][i] = mk(0.0, 0.0);
+            bool converged = !taylor || !p.taylor_check;
+            double rlast = 0.0;
+            bool done[LC];   // per-control early return of taylor_grad_step! (optimize.jl:633-638)
+#pragma unroll
+            for (int l = 0; l < LC; ++l) done[l] = false;
+            for (int sub = 0; sub < (1 << s); ++sub) {
+                cplx ta[N], tb[LC][N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) ta[i] = asum[i];
+#pragma unroll
+                for (int l = 0; l < LC; ++l)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) tb[l][i] = bsum[l][i];
+                for (int j = 1; j <= m; ++j) {
+                    const double inv = 1.0 / (double)j;
+#pragma unroll
+                    for (int l = 0; l < LC; ++l) {
+                        cplx nb[N];
+                        double r2 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                            for (int q = 0; q < N; ++q) cfma(acc, E[l][i * N + q], ta[q]);
+#pragma unroll
+                            for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], tb[l][q]);
+                            nb[i] = cscale(acc, inv);
+                            r2 += cnorm2(nb[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            tb[l][i] = nb[i];
+                            if (!done[l]) bsum[l][i] = cadd(bsum[l][i], nb[i]);
+                        }
+                        if (taylor && p.taylor_check && j >= 2 && !done[l]) {
+                            const double r = sqrt(r2);
+                            rlast = r;
+                            if (r < p.taylor_tol) done[l] = true;
+                        }
+                    }
+                    cplx na[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                        for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], ta[q]);
+                        na[i] = cscale(acc, inv);
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        ta[i] = na[i];
+                        asum[i] = cadd(asum[i], na[i]);
+                    }
+                    if (taylor && p.taylor_check && j >= 2) {
+
+                        bool all_done = true;
+#pragma unroll
+
+                        for (int l = 0; l < LC; ++l) all_done = all_done && done[l];
+
+                        if (all_done) { converged = true; break; }
+
+                    }
+                }
+            }
+            if (act && !converged && p.taylor_max_order > 1) {   // optimize.jl:642-648
+                if (atomicExch(&p.flags->taylor_fail, 1) == 0) p.flags->taylor_r = rlast;
+            }
+#pragma unroll
+            for (int l = 0; l < LC; ++l) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < N; ++i) cfmac(acc, bsum[l][i], psi[i]);
+                tg[l] = cscale(acc, rho);
+            }
+            if (taylor) {
+                // :taylor only defines chi'_l; chi itself is propagated with the full exponential
+                // (prop_step!, optimize.jl:972): converged series independent of taylor_grad_tolerance
+                int mm, ss;
+                vec_plan(sm_norm1<N>(A) * (dt / sc), mm, ss);
+                const double f = ldexp(1.0, -ss);
+#pragma unroll
+                for (int i = 0; i < N; ++i) asum[i] = chi[i];
+                for (int sub = 0; sub < (1 << ss); ++sub) {
+                    cplx ta[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) ta[i] = asum[i];
+                    for (int j = 1; j <= mm; ++j) {
+                        const double inv = f / (double)j;
+                        cplx na[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                            for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], ta[q]);
+                            na[i] = cscale(acc, inv);
+                        }
+#pragma unroll
+                        for (int i = 0; i < N; ++i) { ta[i] = na[i]; asum[i] = cadd(asum[i], na[i]); }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) chi[i] = asum[i];
+        }
+#pragma unroll
+        for (int l = 0; l < LC; ++l) {
+            if (act && p.taugrads) p.taugrads[((size_t)k * p.L + (l0 + l)) * NT + n] = tg[l];
+            red[l] = act ? tg[l].x : 0.0;
+        }
+        // fixed-order sum over the BKL trajectories of this lane group
+#pragma unroll
+        for (int l = 0; l < LC; ++l)
+            for (int off = BKL >> 1; off > 0; off >>= 1)
+                red[l] += __shfl_down_sync(0xffffffffu, red[l], off, BKL);
+        if (tk == 0 && seg < a.NSEG && n >= n0) {
+#pragma unroll
+            for (int l = 0; l < LC; ++l)
+                p.partial[(size_t)kg * p.L * NT + (size_t)(l0 + l) * NT + n] = red[l];
+        }
+    }
+}

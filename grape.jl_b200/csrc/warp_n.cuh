@@ -362,6 +362,9 @@ __global__ void warp_gradient(DevP p, int l0, int spb) {
     const bool taylor = p.grad_method != 0;
     bool converged = !taylor || !p.taylor_check;
     double rlast = 0.0;
+    bool done[LC];
+#pragma unroll
+    for (int l = 0; l < LC; ++l) done[l] = false;
     for (int subst = 0; subst < (1 << s); ++subst) {
         cplx ta = asum, tb[LC];
 #pragma unroll
@@ -385,19 +388,20 @@ __global__ void warp_gradient(DevP p, int l0, int spb) {
                     cfma(nb[l], mk(scl[l] * e.y, scl[l] * e.x), tac);
                 }
             }
-            double r2max = 0.0;
             ta = own ? cscale(na, inv) : mk(0.0, 0.0);
             asum = cadd(asum, ta);
+            bool all_done = true;
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 tb[l] = own ? cscale(nb[l], inv) : mk(0.0, 0.0);
-                bsum[l] = cadd(bsum[l], tb[l]);
-                if (taylor) r2max = fmax(r2max, sub_sum<W>(cnorm2(tb[l]), mask));
+                if (!done[l]) bsum[l] = cadd(bsum[l], tb[l]);
+                if (taylor && p.taylor_check && j >= 2 && !done[l]) {   // per-control early return, optimize.jl:633-638
+                    rlast = sqrt(sub_sum<W>(cnorm2(tb[l]), mask));
+                    if (rlast < p.taylor_tol) done[l] = true;
+                }
+                all_done = all_done && done[l];
             }
-            if (taylor && p.taylor_check && j >= 2) {
-                rlast = sqrt(r2max);
-                if (rlast < p.taylor_tol) { converged = true; break; }
-            }
+            if (taylor && p.taylor_check && j >= 2 && all_done) { converged = true; break; }
         }
     }
     if (!converged && p.taylor_max_order > 1 && r == 0) {

@@ -1,0 +1,154 @@
+"""GPU parity of the time-segmented small-N schedule (csrc/small_seg.cuh) against the CPU
+oracle, against the plain-chain schedule (PATH_SMALL_CHAIN) and across segment lengths.
+Tolerance 1e-10 relative (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import grape.jl_b200 as gb
+from grape.jl_b200 import configs
+from oracle import grape_oracle as go
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def engine(p):
+    from grape.jl_b200.engine import GrapeEngine
+    return GrapeEngine(p)
+
+
+def run(p, eps):
+    e = engine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    return e, J, G
+
+
+def check(p, eps):
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    e, J, G = run(p, eps)
+    scale = max(np.max(np.abs(ref["G"])), 1e-6)
+    assert abs(J - ref["J"]) <= RTOL * max(1.0, abs(ref["J"]))
+    assert np.max(np.abs(G - ref["G"])) <= RTOL * scale
+    assert np.max(np.abs(e.tau_vals - ref["tau"])) <= RTOL
+    for k in range(min(p.K, 3)):
+        assert np.max(np.abs(e.stored_states(k) - ref["storage"][k])) <= 1e-12
+        assert np.max(np.abs(e.tau_grads(k) - ref["tau_grads"][k])) <= 1e-12 * max(1.0, scale)
+    return e, ref, G
+
+
+@pytest.fixture
+def seg_len(request):
+    old = os.environ.get("GRAPE_B200_SEG_S")
+    os.environ["GRAPE_B200_SEG_S"] = str(request.param)
+    yield request.param
+    if old is None:
+        del os.environ["GRAPE_B200_SEG_S"]
+    else:
+        os.environ["GRAPE_B200_SEG_S"] = old
+
+
+@pytest.mark.parametrize("seg_len", [2, 3, 7, 16, 64], indirect=True)
+@pytest.mark.parametrize("N", [1, 2, 3, 4])
+def test_segment_lengths_small_theta(lib_built, seg_len, N):
+    """small ||H dt|| -> Krylov contraction (fast branch) for N <= 3; ragged last segment."""
+    p, eps = configs.random_problem(K=5, N=N, L=2, NT=37, seed=100 + N, hermitian=False, shaped=True,
+                                    functional=gb.SS)
+    p.tlist[:] = p.tlist * 0.02     # theta ~ 1e-2
+    check(p, eps)
+
+
+@pytest.mark.parametrize("seg_len", [2, 5, 64], indirect=True)
+def test_segment_lengths_large_theta(lib_built, seg_len):
+    """||H dt|| ~ O(1): block-recursion branch, with sub-stepping."""
+    p, eps = configs.random_problem(K=7, N=3, L=3, NT=23, seed=7, functional=gb.SM)
+    check(p, eps)
+    p, eps = configs.random_problem(K=3, N=2, L=1, NT=9, seed=8, functional=gb.RE)
+    p.tlist[:] = p.tlist * 30.0
+    check(p, eps)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 31, 32, 33, 70])
+def test_trajectory_counts_lane_mapping(lib_built, K):
+    p, eps = configs.random_problem(K=K, N=3, L=2, NT=21, seed=K, functional=gb.SM, G=min(K, 3))
+    p.tlist[:] = p.tlist * 0.05
+    check(p, eps)
+
+
+def test_matches_plain_chain_schedule(lib_built):
+    for fn in (gb.SM, gb.RE, gb.SS):
+        p, eps = configs.c3_ensemble(n_delta=5, n_amp=9, NT=130, functional=fn)
+        _, J1, G1 = run(p, eps)
+        p2, _ = configs.c3_ensemble(n_delta=5, n_amp=9, NT=130, functional=fn, path=gb.PATH_SMALL_CHAIN)
+        _, J2, G2 = run(p2, eps)
+        assert abs(J1 - J2) <= 1e-13
+        assert np.max(np.abs(G1 - G2)) <= 1e-13 * max(np.max(np.abs(G2)), 1e-6)
+
+
+def test_taylor_method_segmented(lib_built):
+    p, eps = configs.random_problem(K=4, N=3, L=2, NT=19, seed=3, gradient_method=gb.TAYLOR)
+    check(p, eps)
+    # a loose taylor tolerance truncates every chi'_l exactly where taylor_grad_step! returns
+    # (per control, optimize.jl:633-638) and must not affect the propagation of chi itself
+    p, eps = configs.random_problem(K=4, N=3, L=2, NT=19, seed=3, gradient_method=gb.TAYLOR,
+                                    taylor_tolerance=1e-6)
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    _, J, G = run(p, eps)
+    assert np.max(np.abs(G - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+    p2, _ = configs.random_problem(K=4, N=3, L=2, NT=19, seed=3, gradient_method=gb.TAYLOR,
+                                   taylor_tolerance=1e-6, path=gb.PATH_SMALL_CHAIN)
+    _, J2, G2 = run(p2, eps)
+    assert np.max(np.abs(G2 - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+    p3, eps3 = configs.random_problem(K=3, N=7, L=2, NT=11, seed=5, gradient_method=gb.TAYLOR,
+                                     taylor_tolerance=1e-6)
+    ref3 = go.evaluate_gradient(go.from_problem(p3), eps3)
+    _, J3, G3 = run(p3, eps3)
+    assert np.max(np.abs(G3 - ref3["G"])) <= RTOL * np.max(np.abs(ref3["G"]))
+
+
+def test_functional_only_then_stored_states(lib_built):
+    """evaluate_functional skips the interior fill; stored states are produced on demand."""
+    p, eps = configs.c3_ensemble(n_delta=3, n_amp=3, NT=90)
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    e = engine(p)
+    J = e.evaluate_functional(eps)
+    assert abs(J - ref["J"]) <= RTOL
+    assert np.max(np.abs(e.stored_states(4) - ref["storage"][4])) <= 1e-12
+    G = np.zeros_like(eps)
+    e.evaluate_gradient(G, eps)
+    assert np.max(np.abs(G - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+
+
+def test_host_chi_segmented(lib_built):
+    p, eps = configs.c3_ensemble(n_delta=4, n_amp=4, NT=75, functional=gb.HOST)
+    pr, _ = configs.c3_ensemble(n_delta=4, n_amp=4, NT=75, functional=gb.SS)
+    ref = go.evaluate_gradient(go.from_problem(pr), eps)
+    e = engine(p)
+    e.forward(eps)
+    psiT = e.final_states()
+    tau = np.einsum("ki,ki->k", p.tgt.conj(), psiT)
+    Gp = np.zeros_like(eps)
+    e.backward_chi((tau / p.K)[:, None] * p.tgt, Gp)
+    assert np.max(np.abs(Gp - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+
+
+def test_c3_full_size_properties(lib_built):
+    """BASELINE configs[2] at full size: unitarity of the stored states, J_T_ss bounds,
+    gradient finite and deterministic, agreement with the plain-chain schedule."""
+    p, eps = configs.c3_ensemble()
+    e, J, G = run(p, eps)
+    assert 0.0 <= J <= 1.0 and np.all(np.isfinite(G))
+    for k in (0, 1777, 4095):
+        st = e.stored_states(k)
+        assert np.max(np.abs(np.sum(np.abs(st) ** 2, axis=0) - 1.0)) < 1e-12
+    assert abs(J - (1.0 - np.mean(np.abs(e.tau_vals) ** 2))) < 1e-13
+    G2 = np.zeros_like(eps)
+    e.evaluate_gradient(G2, eps)
+    assert np.array_equal(G, G2)
+    e.close()
+    p2, _ = configs.c3_ensemble(path=gb.PATH_SMALL_CHAIN)
+    _, J2, Gc = run(p2, eps)
+    assert abs(J - J2) < 1e-13
+    assert np.max(np.abs(G - Gc)) <= 1e-12 * np.max(np.abs(Gc))

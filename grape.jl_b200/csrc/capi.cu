@@ -12,6 +12,7 @@
 #include "small_seg.cuh"
 #include "warp_n.cuh"
 #include "dense.cuh"
+#include "dense2.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -46,6 +47,7 @@ struct grape_b200_handle_impl {
     int64_t launches;
     WarpPlan warp;
     DensePlan dense;
+    Dense2Plan dense2;
     bool seg_on;          // small path: time-segmented schedule (small_seg.cuh)
     bool interior_done;   // small path, segmented: fw_storage filled inside the segments
     SegArgs seg;
@@ -305,7 +307,10 @@ void run_forward(H* h, bool need_storage = true) {
             SMALL_DISPATCH(h->p.N, small_forward_t<1>(h), small_forward_t<2>(h), small_forward_t<3>(h), small_forward_t<4>(h));
             break;
         case GRAPE_B200_PATH_WARP: warp_run_forward(h->warp, h->p, h->stream, h->launches); break;
-        case GRAPE_B200_PATH_DENSE: dense_run_forward(h->dense, h->p, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_DENSE:
+            if (h->dense2.on) dense2_run_forward(h->dense2, h->dense, h->p, h->stream, h->launches);
+            else dense_run_forward(h->dense, h->p, h->stream, h->launches);
+            break;
     }
     reduce_tau<<<1, 256, 0, h->stream>>>(h->p);
     h->launches++;
@@ -323,7 +328,10 @@ void run_backward(H* h, const cplx* chi_host) {
                            small_backward_t<3>(h, chi_host), small_backward_t<4>(h, chi_host));
             break;
         case GRAPE_B200_PATH_WARP: warp_run_backward(h->warp, h->p, chi_host, h->stream, h->launches); break;
-        case GRAPE_B200_PATH_DENSE: dense_run_backward(h->dense, h->p, chi_host, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_DENSE:
+            if (h->dense2.on) dense2_run_backward(h->dense2, h->dense, h->p, chi_host, h->stream, h->launches);
+            else dense_run_backward(h->dense, h->p, chi_host, h->stream, h->launches);
+            break;
     }
 }
 void run_gradient(H* h) {
@@ -539,6 +547,8 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
         case GRAPE_B200_PATH_DENSE: {
             std::string e;
             rc = dense_setup(h->dense, p, d, h->dev_allocs, e);
+            if (!rc) rc = dense2_setup(h->dense2, h->dense, p, h->dev_allocs, e);
+            if (!rc && !h->dense2.on && !h->dense.strip_ok) { e = h->dense.strip_err; rc = GRAPE_B200_EINVAL; }
             if (rc) h->err = e;
             break;
         }

@@ -56,7 +56,9 @@ struct DensePlan {
     int gridF, gridB;
     size_t smemF, smemB;
     bool ready;
-    DensePlan() : gridF(0), gridB(0), smemF(0), smemB(0), ready(false) {}
+    bool strip_ok;        // the 8-row strip kernels of this file can run (N, K(L+1) small enough)
+    std::string strip_err;
+    DensePlan() : gridF(0), gridB(0), smemF(0), smemB(0), ready(false), strip_ok(true) {}
 };
 
 GB_D void dmma884(double (&acc)[2], double a, double b) {
@@ -595,9 +597,9 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int Np = (N + 31) / 32 * 32, Kp = (K + 7) / 8 * 8, Cb = (L + 1) * Kp;
     d.Np = Np; d.Kp = Kp; d.Cb = Cb; d.RT = Np / 8; d.MS = Np + 4; d.nD = p.gb_nD;
-    if (d.RT > sms) { err = "dense path v1 needs ceil32(N)/8 <= number of SMs (N <= 1184 on B200)"; return GRAPE_B200_EINVAL; }
-    d.Pf = std::max(1, std::min(sms / d.RT, Kp / 8));
-    d.Pb = std::max(1, std::min(sms / d.RT, Cb / 8));
+    if (d.RT > sms) { dp.strip_ok = false; dp.strip_err = "dense strip kernels need ceil32(N)/8 <= number of SMs (N <= 1184 on B200)"; }
+    d.Pf = std::max(1, std::min(std::max(1, sms / d.RT), Kp / 8));
+    d.Pb = std::max(1, std::min(std::max(1, sms / d.RT), Cb / 8));
     d.CcapF = ((Kp / 8 + d.Pf - 1) / d.Pf) * 8;
     d.CcapB = ((Cb / 8 + d.Pb - 1) / d.Pb) * 8;
     dp.gridF = d.RT * d.Pf;
@@ -675,10 +677,12 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     const size_t redB = (size_t)(DENSE_THREADS / 32) * DENSE_CGP * 128;
     dp.smemF = sizeof(double) * (16 * (size_t)d.MS + 16 * (size_t)d.CcapF + redB + d.CcapF + 8);
     dp.smemB = sizeof(double) * (16 * (size_t)d.MS + 16 * (size_t)d.CcapB + redB + 64);
-    if (dp.smemF > 227 * 1024 || dp.smemB > 227 * 1024) { err = "dense path: shared-memory tile does not fit (N or K*(L+1) too large)"; return GRAPE_B200_EINVAL; }
-    cudaError_t e = cudaFuncSetAttribute(dense_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemB);
-    if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e); return GRAPE_B200_ECUDA; }
+    if (dp.smemF > 227 * 1024 || dp.smemB > 227 * 1024) { dp.strip_ok = false; dp.strip_err = "dense strip kernels: shared-memory tile does not fit (N or K*(L+1) too large)"; }
+    if (dp.strip_ok) {
+        cudaError_t e = cudaFuncSetAttribute(dense_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemB);
+        if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e); return GRAPE_B200_ECUDA; }
+    }
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop) { err = "device does not support cooperative launch"; return GRAPE_B200_ECUDA; }

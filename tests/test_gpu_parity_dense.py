@@ -75,3 +75,64 @@ def test_c5_reduced_steps_full_width(lib_built):
     J = e.evaluate_gradient(G, eps)
     assert abs(J - ref["J"]) < 1e-10
     assert np.max(np.abs(G - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
+
+
+# ---- tiled DMMA kernels (csrc/dense2.cuh), forced on problems the oracle finishes quickly
+@pytest.fixture
+def dense2_forced():
+    import os
+    old = os.environ.get("GRAPE_B200_DENSE2")
+    os.environ["GRAPE_B200_DENSE2"] = "1"
+    yield
+    if old is None:
+        del os.environ["GRAPE_B200_DENSE2"]
+    else:
+        os.environ["GRAPE_B200_DENSE2"] = old
+
+
+@pytest.mark.parametrize("N,K", [(33, 9), (64, 16), (100, 12), (130, 27), (40, 32)])
+def test_dense2_random(lib_built, dense2_forced, N, K):
+    p, eps = configs.c4_dense450(N=N, K=K, NT=5)
+    check(p, eps)
+
+
+@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
+@pytest.mark.parametrize("L", [1, 3, 4])
+def test_dense2_functionals_nonhermitian_shaped(lib_built, dense2_forced, functional, L):
+    N, K = 36, 11
+    p, eps = configs.random_problem(K=K, N=N, L=L, NT=5, G=1, seed=170 + functional + 10 * L, hermitian=False,
+                                    shaped=True, weights=np.linspace(0.5, 1.5, K), functional=functional)
+    p.tlist = p.tlist * (0.5 / np.sqrt(N))
+    check(p, eps)
+
+
+def test_dense2_substeps_and_running_costs(lib_built, dense2_forced):
+    p, eps = configs.c4_dense450(N=48, K=10, NT=4)
+    p.tlist = p.tlist * 8.0
+    check(p, eps, rtol=1e-9)
+    p, eps = configs.c5_dense1024(N=40, K=16, NT=7)
+    e, ref = check(p, eps)
+    assert e.J_parts[1] > 0 and e.J_parts[2] > 0
+    assert np.max(np.abs(e.final_states() - ref["final_states"])) < 1e-12
+    assert np.max(np.abs(e.stored_states(3) - ref["storage"][3])) < 1e-12
+
+
+def test_dense2_matches_strip_kernels_c5_width(lib_built):
+    """C5 at full width (N=1024, K=64, J_a + g_b), 2 time steps: tiled kernels (default there)
+    against the strip kernels (GRAPE_B200_DENSE2=0)."""
+    import os
+    p, eps = configs.c5_dense1024(NT=2)
+    e = engine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    e.close()
+    os.environ["GRAPE_B200_DENSE2"] = "0"
+    try:
+        e0 = engine(p)
+        G0 = np.zeros_like(eps)
+        J0 = e0.evaluate_gradient(G0, eps)
+        e0.close()
+    finally:
+        del os.environ["GRAPE_B200_DENSE2"]
+    assert abs(J - J0) <= 1e-12
+    assert np.max(np.abs(G - G0)) <= 1e-11 * np.max(np.abs(G0))

@@ -85,8 +85,8 @@ def c2_transmon(NT=2000, N=6, **kw):
     X = np.eye(N, dtype=np.complex128)
     X[:2, :2] = [[0, 1], [1, 0]]
     tgt = psi0 @ X.T
-    p = GrapeProblem(tlist, H0, np.stack([Hx, Hy]), psi0, tgt, functional=SM,
-                     name="c2_transmon_xgate", **kw)
+    kw.setdefault("functional", SM)
+    p = GrapeProblem(tlist, H0, np.stack([Hx, Hy]), psi0, tgt, name="c2_transmon_xgate", **kw)
     ex = discretize_on_midpoints(lambda t: (np.pi / T) * flattop(t, T=T, t_rise=2.0), tlist)
     ey = np.zeros(NT)
     return p, np.concatenate([ex, ey])

@@ -11,6 +11,7 @@
 #include "small_n.cuh"
 #include "small_seg.cuh"
 #include "warp_n.cuh"
+#include "warp_seg.cuh"
 #include "dense.cuh"
 #include "dense2.cuh"
 
@@ -48,6 +49,8 @@ struct grape_b200_handle_impl {
     WarpPlan warp;
     DensePlan dense;
     Dense2Plan dense2;
+    bool wseg_on;         // warp path: time-segmented schedule (warp_seg.cuh)
+    WarpSegArgs wseg;
     bool seg_on;          // small path: time-segmented schedule (small_seg.cuh)
     bool interior_done;   // small path, segmented: fw_storage filled inside the segments
     SegArgs seg;
@@ -84,6 +87,7 @@ int dev_upload(H* h, T** ptr, const T* src, size_t count) {
 
 int choose_path(int N, int requested) {
     if (requested == GRAPE_B200_PATH_SMALL_CHAIN) return GRAPE_B200_PATH_SMALL;
+    if (requested == GRAPE_B200_PATH_WARP_CHAIN) return GRAPE_B200_PATH_WARP;
     if (requested != GRAPE_B200_PATH_AUTO) return requested;
     if (N <= 4) return GRAPE_B200_PATH_SMALL;
     if (N <= WARP_MAX_N) return GRAPE_B200_PATH_WARP;
@@ -285,13 +289,20 @@ void run_formU(H* h) {
             SMALL_DISPATCH(h->p.N, small_formU_t<1>(h), small_formU_t<2>(h), small_formU_t<3>(h), small_formU_t<4>(h));
             if (h->seg_on) { SMALL_DISPATCH(h->p.N, seg_prod_t<1>(h), seg_prod_t<2>(h), seg_prod_t<3>(h), seg_prod_t<4>(h)); }
             break;
-        case GRAPE_B200_PATH_WARP: warp_run_formU(h->warp, h->p, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_WARP:
+            warp_run_formU(h->warp, h->p, h->stream, h->launches);
+            if (h->wseg_on) warp_seg_run_prod(h->wseg, h->warp, h->p, h->stream, h->launches);
+            break;
         case GRAPE_B200_PATH_DENSE: break;   // dense path never forms U
     }
 }
 void run_fill_interior(H* h) {
     if (h->path == GRAPE_B200_PATH_SMALL && h->seg_on && !h->interior_done) {
         SMALL_DISPATCH(h->p.N, seg_fwd_t<1>(h), seg_fwd_t<2>(h), seg_fwd_t<3>(h), seg_fwd_t<4>(h));
+        h->interior_done = true;
+    }
+    if (h->path == GRAPE_B200_PATH_WARP && h->wseg_on && !h->interior_done) {
+        warp_seg_run_fill(h->wseg, h->warp, h->p, h->stream, h->launches);
         h->interior_done = true;
     }
 }
@@ -306,7 +317,13 @@ void run_forward(H* h, bool need_storage = true) {
             }
             SMALL_DISPATCH(h->p.N, small_forward_t<1>(h), small_forward_t<2>(h), small_forward_t<3>(h), small_forward_t<4>(h));
             break;
-        case GRAPE_B200_PATH_WARP: warp_run_forward(h->warp, h->p, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_WARP:
+            if (h->wseg_on) {
+                warp_seg_run_forward(h->wseg, h->warp, h->p, false, h->stream, h->launches);
+                h->interior_done = false;
+                if (need_storage) run_fill_interior(h);
+            } else warp_run_forward(h->warp, h->p, h->stream, h->launches);
+            break;
         case GRAPE_B200_PATH_DENSE:
             if (h->dense2.on) dense2_run_forward(h->dense2, h->dense, h->p, h->stream, h->launches);
             else dense_run_forward(h->dense, h->p, h->stream, h->launches);
@@ -327,7 +344,12 @@ void run_backward(H* h, const cplx* chi_host) {
             SMALL_DISPATCH(h->p.N, small_backward_t<1>(h, chi_host), small_backward_t<2>(h, chi_host),
                            small_backward_t<3>(h, chi_host), small_backward_t<4>(h, chi_host));
             break;
-        case GRAPE_B200_PATH_WARP: warp_run_backward(h->warp, h->p, chi_host, h->stream, h->launches); break;
+        case GRAPE_B200_PATH_WARP:
+            if (h->wseg_on) {
+                run_fill_interior(h);
+                warp_seg_run_backward(h->wseg, h->warp, h->p, chi_host, h->stream, h->launches);
+            } else warp_run_backward(h->warp, h->p, chi_host, h->stream, h->launches);
+            break;
         case GRAPE_B200_PATH_DENSE:
             if (h->dense2.on) dense2_run_backward(h->dense2, h->dense, h->p, chi_host, h->stream, h->launches);
             else dense_run_backward(h->dense, h->p, chi_host, h->stream, h->launches);
@@ -472,6 +494,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
+    h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     h->device = d->device;
     auto bail = [&](int rc) {
         g_create_error = h->err;
@@ -541,6 +564,9 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
         case GRAPE_B200_PATH_WARP: {
             std::string e;
             rc = warp_setup(h->warp, p, d, h->dev_allocs, e);
+            // time-segmented schedule unless a state running cost couples chi to Psi at every step
+            h->wseg_on = !rc && p.gb_kind == 0 && d->path != GRAPE_B200_PATH_WARP_CHAIN;
+            if (h->wseg_on) rc = warp_seg_setup(h->wseg, h->warp, p, h->dev_allocs, e);
             if (rc) h->err = e;
             break;
         }

@@ -37,6 +37,7 @@ constexpr int DENSE_THREADS = 256;
 
 struct DenseDev {
     int Np, Kp, Cb, RT, Pf, Pb, MS, CcapF, CcapB, nD;
+    int mu_smem;   // backward strip kernel keeps its 8 rows of every mu_l^dagger in shared memory
     const double* Hf;
     const double* Ha;
     const double* Dm;
@@ -84,8 +85,8 @@ GB_D void dense_mma_slice(const double* __restrict__ Bre, const double* __restri
     for (int k0 = kbeg; k0 < kend; k0 += 4) {
         double bre, bim;
         if (BSMEM) {
-            bre = Bre[lr * bstride + k0 + lc];
-            bim = Bim[lr * bstride + k0 + lc];
+            bre = bscale * Bre[lr * bstride + k0 + lc];
+            bim = bscale * Bim[lr * bstride + k0 + lc];
         } else {
             bre = bscale * __ldg(&Bre[(size_t)lr * bstride + k0 + lc]);
             bim = bscale * __ldg(&Bim[(size_t)lr * bstride + k0 + lc]);
@@ -314,6 +315,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
     double* acc_im = acc_re + 8 * Ccap;
     double* red = acc_im + 8 * Ccap;
     double* s_buf = red + (DENSE_THREADS / 32) * DENSE_CGP * 128;   // 32 doubles for block_sum
+    double* Mu_s = s_buf + 64;                                      // [L][2][8][MS] if d.mu_smem
     const size_t bplane = (size_t)Np * Cb, splane = (size_t)Np * Kp, hplane = (size_t)Np * Np;
     const int w = threadIdx.x >> 5;
     const int kslice = Np / 8, kbeg = w * kslice, kend = kbeg + kslice;
@@ -324,6 +326,13 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
         const int r = e / ncols, c = e % ncols;
         acc_re[r * Ccap + c] = d.bcur[(size_t)(r0 + r) * Cb + cbeg + c];
         acc_im[r * Ccap + c] = d.bcur[bplane + (size_t)(r0 + r) * Cb + cbeg + c];
+    }
+    if (d.mu_smem) {   // the control operators do not depend on the time step: staged once
+        for (int e = threadIdx.x; e < L * 2 * 8 * Np; e += DENSE_THREADS) {
+            const int k = e % Np, r = (e / Np) % 8, pl = (e / (8 * Np)) % 2, l = e / (16 * Np);
+            Mu_s[((size_t)(l * 2 + pl) * 8 + r) * MS + k] =
+                d.Ha[(size_t)(1 + l) * 2 * hplane + (size_t)pl * hplane + (size_t)(r0 + r) * Np + k];
+        }
     }
     __syncthreads();
 
@@ -358,8 +367,13 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
                                 DAcc a1[1];
                                 a1[0] = acc[g];
                                 const double sl = p.shape ? p.shape[l * NT + n] : 1.0;
-                                const double* Bl = d.Ha + (size_t)(1 + l) * 2 * hplane + (size_t)r0 * Np;
-                                dense_mma_slice<1, false>(Bl, Bl + hplane, Np, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
+                                if (d.mu_smem) {
+                                    const double* Ml = Mu_s + (size_t)(l * 2) * 8 * MS;
+                                    dense_mma_slice<1, true>(Ml, Ml + 8 * MS, MS, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
+                                } else {
+                                    const double* Bl = d.Ha + (size_t)(1 + l) * 2 * hplane + (size_t)r0 * Np;
+                                    dense_mma_slice<1, false>(Bl, Bl + hplane, Np, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
+                                }
                                 acc[g] = a1[0];
                             }
                         }
@@ -677,6 +691,11 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     const size_t redB = (size_t)(DENSE_THREADS / 32) * DENSE_CGP * 128;
     dp.smemF = sizeof(double) * (16 * (size_t)d.MS + 16 * (size_t)d.CcapF + redB + d.CcapF + 8);
     dp.smemB = sizeof(double) * (16 * (size_t)d.MS + 16 * (size_t)d.CcapB + redB + 64);
+    d.mu_smem = 0;
+    if (dp.smemB + sizeof(double) * (size_t)L * 16 * d.MS <= 220 * 1024) {
+        d.mu_smem = 1;
+        dp.smemB += sizeof(double) * (size_t)L * 16 * d.MS;
+    }
     if (dp.smemF > 227 * 1024 || dp.smemB > 227 * 1024) { dp.strip_ok = false; dp.strip_err = "dense strip kernels: shared-memory tile does not fit (N or K*(L+1) too large)"; }
     if (dp.strip_ok) {
         cudaError_t e = cudaFuncSetAttribute(dense_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);

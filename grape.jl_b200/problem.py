@@ -9,7 +9,7 @@ SM, RE, SS, HOST = 0, 1, 2, 3
 GRADGEN, TAYLOR = 0, 1
 JA_NONE, JA_FLUENCE = 0, 1
 GB_NONE, GB_QUADFORM = 0, 1
-PATH_AUTO, PATH_SMALL, PATH_WARP, PATH_DENSE, PATH_SMALL_CHAIN = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_SMALL, PATH_WARP, PATH_DENSE, PATH_SMALL_CHAIN, PATH_WARP_CHAIN = 0, 1, 2, 3, 4, 5
 
 
 class GrapeProblem:

@@ -79,6 +79,7 @@ extern "C" {
 #define GRAPE_B200_PATH_WARP   2  /* N <= 32: sub-warp per (trajectory, step), shuffles     */
 #define GRAPE_B200_PATH_DENSE  3  /* any N: polynomial apply on state blocks, DMMA ZGEMM    */
 #define GRAPE_B200_PATH_SMALL_CHAIN 4 /* N <= 4 with plain NT-step chains (no time segmentation) */
+#define GRAPE_B200_PATH_WARP_CHAIN  5 /* N <= 32 with plain NT-step chains (no time segmentation) */
 
 /* Problem descriptor = the hot fields of GrapeWrk (src/workspace.jl:78-144). */
 typedef struct grape_b200_problem {

@@ -152,3 +152,42 @@ def test_c3_full_size_properties(lib_built):
     _, J2, Gc = run(p2, eps)
     assert abs(J - J2) < 1e-13
     assert np.max(np.abs(G - Gc)) <= 1e-12 * np.max(np.abs(Gc))
+
+
+# ---------------------------------------------------------------- sub-warp path (5 <= N <= 32)
+@pytest.mark.parametrize("seg_len", [2, 3, 7, 128], indirect=True)
+@pytest.mark.parametrize("N", [5, 6, 9, 16, 17, 32])
+def test_warp_segment_lengths(lib_built, seg_len, N):
+    p, eps = configs.random_problem(K=5, N=N, L=2, NT=23, seed=200 + N, hermitian=False, shaped=True,
+                                    functional=gb.SM, G=2)
+    p.tlist[:] = p.tlist * (0.6 / np.sqrt(N))
+    check(p, eps)
+
+
+def test_warp_matches_plain_chain_schedule(lib_built):
+    p, eps = configs.c2_transmon(NT=300)
+    e, J1, G1 = run(p, eps)
+    p2, _ = configs.c2_transmon(NT=300, path=gb.PATH_WARP_CHAIN)
+    _, J2, G2 = run(p2, eps)
+    assert abs(J1 - J2) <= 1e-13
+    assert np.max(np.abs(G1 - G2)) <= 1e-12 * np.max(np.abs(G2))
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    assert np.max(np.abs(G1 - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+    chi, rho = e.chi_states()
+    assert np.max(np.abs(chi - ref["chi_states"])) < 1e-12
+
+
+def test_warp_functional_only_and_host_chi(lib_built):
+    p, eps = configs.c2_transmon(NT=120)
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    e = engine(p)
+    assert abs(e.evaluate_functional(eps) - ref["J"]) <= RTOL
+    assert np.max(np.abs(e.stored_states(2) - ref["storage"][2])) <= 1e-12
+    ph, _ = configs.c2_transmon(NT=120, functional=gb.HOST)
+    eh = engine(ph)
+    eh.forward(eps)
+    tau = np.einsum("ki,ki->k", ph.tgt.conj(), eh.final_states())
+    chi = (np.sum(tau) / ph.K ** 2) * ph.tgt          # J_T_sm: chi_k = (sum_j tau_j / K^2) |tgt_k>
+    Gp = np.zeros_like(eps)
+    eh.backward_chi(chi, Gp)
+    assert np.max(np.abs(Gp - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))

@@ -292,7 +292,7 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak_src = "of measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "of fallback 6650 GB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_per_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
                 dtype="f64 (complex128)", data="synthetic",
@@ -305,22 +305,46 @@ def main():
         names = ["propagator_formation", "forward_sweep", "tau", "backward_sweep", "gradient_contraction"]
         dom = int(np.argmax(phase[:5]))
         k_ms = float(phase[dom])
-        b_unit = 32 * p.N + 16 * p.L            # SURVEY 8d algorithmic bytes per unit
-        achieved = b_unit * units_per_step / (k_ms * 1e-3) / 1e9
-        line["roofline"] = dict(bound="hbm", kernel=names[dom], achieved=achieved, peak=hbm_peak, unit="GB/s",
-                                frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
-                                kernel_ms=k_ms, algorithmic_bytes_per_unit=b_unit,
-                                phase_ms=dict(zip(names, [float(v) for v in phase[:5]])),
-                                share_of_step=k_ms / float(phase[6]) if phase[6] > 0 else None)
         fp = pk.measure(local_rank)
-        fl_unit = pk.executed_flops_per_unit(p, eps)
-        line["roofline_fp64"] = dict(
-            bound="fp64_fma", note="the small-N kernels are FP64-FMA bound, not HBM bound (SURVEY 8d); "
-                                   "flops are the DFMA work the kernels execute (model in DESIGN.md), step-level",
-            achieved=fl_unit * units_per_step / (ms_per_step * 1e-3) / 1e12, unit="TFLOP/s",
-            peak=fp["dfma_tflops"], peak_source="measured on this GPU (csrc/peaks.cu DFMA loop)",
-            dmma_peak=fp["dmma_tflops"], flops_per_unit=fl_unit,
-            frac=fl_unit * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dfma_tflops"] if fp["dfma_tflops"] > 0 else None)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            if tj and tj.get("phase") == names[dom]:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
+        if p.N > 32:
+            # dense path: FP64 tensor-core (DMMA) roofline; peak measured on this GPU in this run
+            f_fwd, f_bwd, terms = pk.dense_flops_per_unit(p, eps)
+            share = {1: f_fwd, 3: f_bwd}.get(dom, 0.0)
+            achieved = share * units_per_step / (k_ms * 1e-3) / 1e12
+            line["roofline"] = dict(
+                bound="tensor", kernel=names[dom] + (" (dense2_backward / dense_backward, DMMA m8n8k4)" if dom == 3 else ""),
+                achieved=achieved, peak=fp["dmma_tflops"], unit="TFLOP/s",
+                frac=achieved / fp["dmma_tflops"] if fp["dmma_tflops"] > 0 else None, traffic=traffic,
+                peak_source="FP64 DMMA peak measured on this GPU in this run (csrc/peaks.cu); MEASURED_PEAKS.json "
+                            "carries no FP64 figure",
+                kernel_ms=k_ms, flops_per_unit_kernel=share, flops_per_unit_step=f_fwd + f_bwd, taylor_terms=terms,
+                step_tflops=(f_fwd + f_bwd) * units_per_step / (ms_per_step * 1e-3) / 1e12,
+                step_frac=(f_fwd + f_bwd) * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dmma_tflops"],
+                phase_ms=dict(zip(names, [float(v) for v in phase[:5]])),
+                share_of_step=k_ms / float(phase[6]) if phase[6] > 0 else None)
+        else:
+            b_unit = 32 * p.N + 16 * p.L            # SURVEY 8d algorithmic bytes per unit
+            achieved = b_unit * units_per_step / (k_ms * 1e-3) / 1e9
+            line["roofline"] = dict(bound="hbm", kernel=names[dom], achieved=achieved, peak=hbm_peak, unit="GB/s",
+                                    frac=achieved / hbm_peak, traffic=traffic, traffic_source=traffic_src,
+                                    peak_source=peak_src, kernel_ms=k_ms, algorithmic_bytes_per_unit=b_unit,
+                                    phase_ms=dict(zip(names, [float(v) for v in phase[:5]])),
+                                    share_of_step=k_ms / float(phase[6]) if phase[6] > 0 else None)
+            fl_unit = pk.executed_flops_per_unit(p, eps)
+            line["roofline_fp64"] = dict(
+                bound="fp64_fma", note="the small-N kernels are FP64-FMA bound, not HBM bound (SURVEY 8d); "
+                                       "flops are the FP64 work the kernels execute (model in grape.jl_b200/peaks.py), step-level",
+                achieved=fl_unit * units_per_step / (ms_per_step * 1e-3) / 1e12, unit="TFLOP/s",
+                peak=fp["dfma_tflops"], peak_source="measured on this GPU in this run (csrc/peaks.cu DFMA loop)",
+                dmma_peak=fp["dmma_tflops"], flops_per_unit=fl_unit,
+                frac=fl_unit * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dfma_tflops"] if fp["dfma_tflops"] > 0 else None)
         if not args.no_cpu_baseline:
             sk, snt = cpu_sample_size(args.workload)
             cb, _ = cpu_reference_run(p, eps, sk, snt, 1, 1)

@@ -38,11 +38,7 @@ def _vec_terms(nrm):
     return np.maximum(m, 2), s
 
 
-def executed_flops_per_unit(p, eps, sample=64):
-    """Real FP64 flops per (trajectory, step) unit executed by the small-N / warp
-    kernels (complex FMA = 8 flops): propagator formation by Paterson-Stockmeyer
-    Taylor (per generator-step, amortised over the trajectories sharing it),
-    two chain mat-vecs, and the (1+2L)-mat-vec block recursion with m terms."""
+def _plans(p, eps, sample=64):
     N, L, NT, K, G = p.N, p.L, p.NT, p.K, p.G
     gs = np.unique(np.linspace(0, G - 1, min(G, sample)).astype(int))
     e = np.asarray(eps).reshape(L, NT)
@@ -51,14 +47,56 @@ def executed_flops_per_unit(p, eps, sample=64):
     dt = np.diff(p.tlist)
     H = p.H0[gs][:, None] + np.einsum("ln,glij->gnij", e, p.Hc[gs])
     nrm = np.max(np.sum(np.abs(H.real) + np.abs(H.imag), axis=2), axis=2) * dt[None, :]
+    return nrm
+
+
+def executed_flops_per_unit(p, eps, sample=64):
+    """FP64 flops per (trajectory, step) unit that the small-N / sub-warp kernels execute
+    (complex FMA = 8 flops, real-times-complex FMA = 4), following the kernels' own plans:
+    propagator formation by Paterson-Stockmeyer Taylor + segment product (per generator-step,
+    amortised over the trajectories sharing the generator), the segment fill mat-vecs, and the
+    gradient contraction -- Krylov form (small_seg.cuh, m <= 8, no sub-steps, N <= 3, :gradgen)
+    or the (1+2L)-mat-vec block recursion with m terms."""
+    N, L, NT, K, G = p.N, p.L, p.NT, p.K, p.G
+    nrm = _plans(p, eps, sample)
     deg, s = _exp_plan(nrm)
     bs = 4 if N <= 3 else 2
     if bs == 4:
         prods = np.where(deg == 3, 2, 3 + (deg + 1) // 4 - 1)
     else:
         prods = 1 + (deg + 1) // 2 - 1
-    a_flops = np.mean((prods + s) * 8.0 * N ** 3) * G / K
+    seg = p.gb_kind == 0 and N <= 32
+    a_flops = (np.mean((prods + s) * 8.0 * N ** 3) + 4.0 * L * N * N + (8.0 * N ** 3 if seg else 0.0)) * G / K
     m, sv = _vec_terms(nrm)
-    c_flops = np.mean(m * (2.0 ** sv) * (1 + 2 * L) * 8.0 * N * N) + L * 8.0 * N
-    b_flops = 2 * 8.0 * N * N
+    rec = m * (2.0 ** sv) * (1 + 2 * L) * 8.0 * N * N + L * 8.0 * N
+    if seg and N <= 3 and p.gradient_method == 0:
+        mm = np.minimum(m, 8)
+        eacc = sum(np.where(a < mm, (8 - a) * 4.0 * N, 0.0) for a in range(1, 8)) + 8 * 2.0 * N
+        kry = (2 * mm - 1) * 8.0 * N * N + eacc + mm * 8.0 * N * N + mm * 2.0 * N + L * 8.0 * N * N + 4.0 * L * N * N
+        fast = (sv == 0) & (m <= 8)
+        c_flops = np.mean(np.where(fast, kry, rec))
+    else:
+        c_flops = np.mean(rec)
+    b_flops = 2 * 8.0 * N * N          # forward fill / chain + backward fill / chain mat-vecs
+    if seg and N <= 4:
+        b_flops = 8.0 * N * N          # chi is carried inside the contraction kernel
     return float(a_flops + b_flops + c_flops)
+
+
+def dense_flops_per_unit(p, eps):
+    """Flops per unit of the dense (polynomial-apply) path, split (forward, backward):
+    8 N^2 m per state column and Taylor term; backward has (1 + 2L) columns per trajectory
+    (H^dagger on L+1 blocks, mu_l^dagger on chi); + one D Psi product per step each way with g_b.
+    m follows dense_plan() (spectral-norm bound * 1.05)."""
+    N, L, NT = p.N, p.L, p.NT
+    e = np.abs(np.asarray(eps).reshape(L, NT))
+    if p.shape is not None:
+        e = e * np.abs(p.shape)
+    hn = [1.05 * np.linalg.norm(p.H0[0], 2)] + [1.05 * np.linalg.norm(p.Hc[0, l], 2) for l in range(L)]
+    nrm = (hn[0] + sum(e[l] * hn[1 + l] for l in range(L))) * np.diff(p.tlist)
+    m, sv = _vec_terms(nrm)
+    terms = float(np.mean(m * 2.0 ** sv))
+    gbf = 8.0 * N * N if p.gb_kind else 0.0
+    fwd = 8.0 * N * N * terms + gbf
+    bwd = 8.0 * N * N * terms * (1 + 2 * L) + gbf
+    return fwd, bwd, terms

@@ -17,16 +17,6 @@ struct WarpSegArgs {
     cplx* Pseg;   // [NSEG][G][N*N] row-major
 };
 
-// pull one N x N matrix (L2-resident) into L1 a few steps before it is needed: the chains are pure
-// latency, and a one-step-ahead register prefetch still exposes one L2 round trip per step
-constexpr int WSEG_PFD = 6;
-template <int W>
-GB_D void wseg_prefetch(const cplx* __restrict__ M, int NN, int r) {
-    const int lines = (NN * (int)sizeof(cplx) + 127) / 128;
-    const char* base = reinterpret_cast<const char*>(M);
-    for (int l = r; l < lines; l += W) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)l * 128));
-}
-
 // ---------------------------------------------------------------------------
 // segment propagators: P = U_{n1-1} ... U_{n0}; sub-warp per (g, seg); matrices in shared memory
 // ---------------------------------------------------------------------------
@@ -57,6 +47,16 @@ __global__ void warp_segprod(DevP p, WarpSegArgs a, int spb) {
     }
     cplx* o = a.Pseg + ((size_t)seg * G + g) * NN;
     for (int e = r; e < NN; e += W) o[e] = P[e];
+}
+
+// pull one N x N matrix (L2-resident) into L1 a few steps before it is needed: the chains are pure
+// latency, and a one-step-ahead register prefetch still exposes one L2 round trip per step
+constexpr int WSEG_PFD = 6;
+template <int W>
+GB_D void wseg_prefetch(const cplx* __restrict__ M, int NN, int r) {
+    const int lines = (NN * (int)sizeof(cplx) + 127) / 128;
+    const char* base = reinterpret_cast<const char*>(M);
+    for (int l = r; l < lines; l += W) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)l * 128));
 }
 
 // y_r = sum_j M[r][j] x_j (row r in u[]) or sum_j conj(M[j][r]) x_j (column r in u[])

@@ -37,9 +37,7 @@ __global__ void warp_segprod(DevP p, WarpSegArgs a, int spb) {
     const size_t ustride = (size_t)G * NN;
     for (int e = r; e < NN; e += W) P[e] = Ug[(size_t)n0 * ustride + e];
     __syncwarp(mask);
-    for (int n = n0 + 1; n < min(n1, n0 + 1 + WSEG_PFD); ++n) wseg_prefetch<W>(Ug + (size_t)n * ustride, NN, r);
     for (int n = n0 + 1; n < n1; ++n) {
-        if (n + WSEG_PFD < n1) wseg_prefetch<W>(Ug + (size_t)(n + WSEG_PFD) * ustride, NN, r);
         for (int e = r; e < NN; e += W) Us[e] = Ug[(size_t)n * ustride + e];
         __syncwarp(mask);
         sw_matmul<W>(T, Us, P, N, r, mask);   // T = U_n * P
@@ -47,16 +45,6 @@ __global__ void warp_segprod(DevP p, WarpSegArgs a, int spb) {
     }
     cplx* o = a.Pseg + ((size_t)seg * G + g) * NN;
     for (int e = r; e < NN; e += W) o[e] = P[e];
-}
-
-// pull one N x N matrix (L2-resident) into L1 a few steps before it is needed: the chains are pure
-// latency, and a one-step-ahead register prefetch still exposes one L2 round trip per step
-constexpr int WSEG_PFD = 6;
-template <int W>
-GB_D void wseg_prefetch(const cplx* __restrict__ M, int NN, int r) {
-    const int lines = (NN * (int)sizeof(cplx) + 127) / 128;
-    const char* base = reinterpret_cast<const char*>(M);
-    for (int l = r; l < lines; l += W) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + (size_t)l * 128));
 }
 
 // y_r = sum_j M[r][j] x_j (row r in u[]) or sum_j conj(M[j][r]) x_j (column r in u[])
@@ -112,10 +100,8 @@ __global__ void __launch_bounds__(128) warp_seg_fwd(DevP p, WarpSegArgs a) {
         if (n1 - n0 < 2) return;
         const cplx* Ug = p.U + (size_t)g * NN;
         cplx x = own ? p.psi[((size_t)n0 * K + k) * N + r] : mk(0.0, 0.0);
-        for (int n = n0; n < min(n1 - 1, n0 + WSEG_PFD); ++n) wseg_prefetch<W>(Ug + (size_t)n * mstride, NN, r);
         if (PF) wseg_load<W, false>(un, Ug + (size_t)n0 * mstride, N, rr);
         for (int n = n0; n < n1 - 1; ++n) {
-            if (n + WSEG_PFD < n1 - 1) wseg_prefetch<W>(Ug + (size_t)(n + WSEG_PFD) * mstride, NN, r);
             if (PF) {
 #pragma unroll
                 for (int j = 0; j < W; ++j) u[j] = un[PF ? j : 0];
@@ -129,10 +115,8 @@ __global__ void __launch_bounds__(128) warp_seg_fwd(DevP p, WarpSegArgs a) {
         const cplx* Pg = a.Pseg + (size_t)g * NN;
         cplx x = own ? p.psi0[(size_t)k * N + r] : mk(0.0, 0.0);
         if (own) p.psi[(size_t)k * N + r] = x;
-        for (int q = 0; q < min(a.NSEG, WSEG_PFD); ++q) wseg_prefetch<W>(Pg + (size_t)q * mstride, NN, r);
         if (PF) wseg_load<W, false>(un, Pg, N, rr);
         for (int q = 0; q < a.NSEG; ++q) {
-            if (q + WSEG_PFD < a.NSEG) wseg_prefetch<W>(Pg + (size_t)(q + WSEG_PFD) * mstride, NN, r);
             if (PF) {
 #pragma unroll
                 for (int j = 0; j < W; ++j) u[j] = un[PF ? j : 0];
@@ -176,10 +160,8 @@ __global__ void __launch_bounds__(128) warp_seg_bwd(DevP p, WarpSegArgs a, const
         if (n1 - n0 < 2) return;
         const cplx* Ug = p.U + (size_t)g * NN;
         cplx x = own ? p.chi[((size_t)n1 * K + k) * N + r] : mk(0.0, 0.0);
-        for (int n = n1 - 1; n > max(n0, n1 - 1 - WSEG_PFD); --n) wseg_prefetch<W>(Ug + (size_t)n * mstride, NN, r);
         if (PF) wseg_load<W, true>(un, Ug + (size_t)(n1 - 1) * mstride, N, rr);
         for (int n = n1 - 1; n > n0; --n) {
-            if (n - WSEG_PFD > n0) wseg_prefetch<W>(Ug + (size_t)(n - WSEG_PFD) * mstride, NN, r);
             if (PF) {
 #pragma unroll
                 for (int j = 0; j < W; ++j) u[j] = un[PF ? j : 0];
@@ -191,7 +173,6 @@ __global__ void __launch_bounds__(128) warp_seg_bwd(DevP p, WarpSegArgs a, const
         }
     } else {
         const cplx* Pg = a.Pseg + (size_t)g * NN;
-        for (int q = a.NSEG - 1; q >= max(1, a.NSEG - WSEG_PFD); --q) wseg_prefetch<W>(Pg + (size_t)q * mstride, NN, r);
         if (PF && a.NSEG > 1) wseg_load<W, true>(un, Pg + (size_t)(a.NSEG - 1) * mstride, N, rr);
         // boundary condition chi_k(T) (reference src/optimize.jl:845-869)
         cplx x;
@@ -217,7 +198,6 @@ __global__ void __launch_bounds__(128) warp_seg_bwd(DevP p, WarpSegArgs a, const
             p.chi[((size_t)NT * K + k) * N + r] = x;
         }
         for (int q = a.NSEG - 1; q >= 1; --q) {
-            if (q - WSEG_PFD >= 1) wseg_prefetch<W>(Pg + (size_t)(q - WSEG_PFD) * mstride, NN, r);
             if (PF) {
 #pragma unroll
                 for (int j = 0; j < W; ++j) u[j] = un[PF ? j : 0];
@@ -287,3 +267,4 @@ inline void warp_seg_run_backward(const WarpSegArgs& a, const WarpPlan& wp, cons
     }
     launches += 2;
 }
+

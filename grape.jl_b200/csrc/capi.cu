@@ -49,6 +49,11 @@ struct grape_b200_handle_impl {
     WarpPlan warp;
     DensePlan dense;
     Dense2Plan dense2;
+    // CUDA graphs of the complete eval_f / eval_fg call (H2D, kernel sequence, D2H): the small and
+    // sub-warp paths launch ~10 short kernels per call and are launch-bound for few trajectories
+    cudaGraphExec_t graph_fg, graph_f;
+    int64_t graph_fg_launches, graph_f_launches;
+    bool graphs_ok;
     bool wseg_on;         // warp path: time-segmented schedule (warp_seg.cuh)
     WarpSegArgs wseg;
     bool seg_on;          // small path: time-segmented schedule (small_seg.cuh)
@@ -434,6 +439,45 @@ int download_all(H* h) {
     return 0;
 }
 
+// Whole-call CUDA graph (small / sub-warp paths, profiling off). Returns 1 if the call was served
+// by a graph launch, 0 if the caller must launch directly, < 0 on error (code negated).
+int eval_via_graph(H* h, const double* pulsevals, bool grad) {
+    if (!h->graphs_ok || h->profiling || h->path == GRAPE_B200_PATH_DENSE) return 0;
+    cudaGraphExec_t& ge = grad ? h->graph_fg : h->graph_f;
+    int64_t& gl = grad ? h->graph_fg_launches : h->graph_f_launches;
+    memcpy(h->h_in, pulsevals, sizeof(double) * h->LNT);
+    h->p.eps = h->d_eps_own;
+    if (!ge) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError(); h->graphs_ok = false; return 0;
+        }
+        const int64_t l0 = h->launches;
+        cudaMemcpyAsync(h->d_eps_own, h->h_in, sizeof(double) * h->LNT, cudaMemcpyHostToDevice, h->stream);
+        cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream);
+        run_formU(h);
+        run_forward(h, grad);
+        if (grad) { run_backward(h, nullptr); run_gradient(h); }
+        run_finalize(h, grad);
+        cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * h->out_doubles, cudaMemcpyDeviceToHost, h->stream);
+        gl = h->launches - l0;
+        h->launches = l0;
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&ge, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (e != cudaSuccess) { cudaGetLastError(); ge = nullptr; h->graphs_ok = false; return 0; }
+    }
+    if (cudaGraphLaunch(ge, h->stream) != cudaSuccess) { cudaGetLastError(); h->graphs_ok = false; return 0; }
+    h->launches += gl;
+    // the captured sequence of eval_f leaves the interior of fw_storage unfilled
+    if (h->seg_on || h->wseg_on) h->interior_done = grad;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        h->err = "CUDA error while executing the evaluation graph";
+        return -GRAPE_B200_ECUDA;
+    }
+    return 1;
+}
+
 }  // namespace
 
 struct grape_b200_handle : grape_b200_handle_impl {};
@@ -450,6 +494,8 @@ void grape_b200_destroy(grape_b200_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->graph_fg) cudaGraphExecDestroy(h->graph_fg);
+    if (h->graph_f) cudaGraphExecDestroy(h->graph_f);
     dense_destroy(h->dense);
     for (void* q : h->dev_allocs) cudaFree(q);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -495,6 +541,8 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
+    h->graph_fg = nullptr; h->graph_f = nullptr; h->graph_fg_launches = h->graph_f_launches = 0;
+    h->graphs_ok = !(getenv("GRAPE_B200_NO_GRAPH") && atoi(getenv("GRAPE_B200_NO_GRAPH")) != 0);
     h->device = d->device;
     auto bail = [&](int rc) {
         g_create_error = h->err;
@@ -597,13 +645,17 @@ int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals, double* J_p
     if (!h || !pulsevals) return GRAPE_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int64_t l0 = h->launches;
-    rec(h, 0);
-    if (int rc = upload_pulses(h, pulsevals)) return rc;
-    run_formU(h); rec(h, 1);
-    run_forward(h, false); rec(h, 2);   // interior of fw_storage is filled lazily (get_stored_states)
-    run_finalize(h, false); rec(h, 3); rec(h, 4); rec(h, 5);
-    if (int rc = download_all(h)) return rc;
-    collect_timings(h, l0);
+    const int via = eval_via_graph(h, pulsevals, false);
+    if (via < 0) return -via;
+    if (!via) {
+        rec(h, 0);
+        if (int rc = upload_pulses(h, pulsevals)) return rc;
+        run_formU(h); rec(h, 1);
+        run_forward(h, false); rec(h, 2);   // interior of fw_storage is filled lazily (get_stored_states)
+        run_finalize(h, false); rec(h, 3); rec(h, 4); rec(h, 5);
+        if (int rc = download_all(h)) return rc;
+        collect_timings(h, l0);
+    }
     h->forward_done = true; h->backward_done = false;
     if (h->p.functional == GRAPE_B200_JT_HOST) h->h_out[h->off_J] = 0.0 / 0.0;
     copy_out_common(h, J_parts, tau);
@@ -619,16 +671,20 @@ int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G,
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int64_t l0 = h->launches;
-    rec(h, 0);
-    if (int rc = upload_pulses(h, pulsevals)) return rc;
-    run_formU(h); rec(h, 1);
-    run_forward(h); rec(h, 2);
-    rec(h, 3);
-    run_backward(h, nullptr); rec(h, 4);
-    run_gradient(h);
-    run_finalize(h, true); rec(h, 5);
-    if (int rc = download_all(h)) return rc;
-    collect_timings(h, l0);
+    const int via = eval_via_graph(h, pulsevals, true);
+    if (via < 0) return -via;
+    if (!via) {
+        rec(h, 0);
+        if (int rc = upload_pulses(h, pulsevals)) return rc;
+        run_formU(h); rec(h, 1);
+        run_forward(h); rec(h, 2);
+        rec(h, 3);
+        run_backward(h, nullptr); rec(h, 4);
+        run_gradient(h);
+        run_finalize(h, true); rec(h, 5);
+        if (int rc = download_all(h)) return rc;
+        collect_timings(h, l0);
+    }
     h->forward_done = true; h->backward_done = true;
     const int LNT = h->LNT;
     memcpy(G, h->h_out, sizeof(double) * LNT);

@@ -81,7 +81,7 @@ GB_D void dense_mma_slice(const double* __restrict__ Bre, const double* __restri
                           int ldx, const int (&col0)[NG], int ng, int kbeg, int kend, DAcc (&acc)[NG]) {
     const int lane = threadIdx.x & 31;
     const int lr = lane >> 2, lc = lane & 3;
-#pragma unroll 2
+#pragma unroll 4
     for (int k0 = kbeg; k0 < kend; k0 += 4) {
         double bre, bim;
         if (BSMEM) {

@@ -933,6 +933,8 @@ void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which) {
         case 1: return h->p.sums;
         case 2: return h->d_eps_own;
         case 3: return h->p.grad;            // full G
+        case 4: return h->p.Jparts;          // J_parts[3]
+        case 5: return h->p.tau;             // tau[K] complex (local trajectories)
     }
     return nullptr;
 }

@@ -37,6 +37,16 @@ class ShardedGrape:
         self._sums = torch.zeros(4, **kw)
         self._grad = torch.zeros(LNT, **kw)
         self._G_partial = np.zeros(LNT)
+        # device-resident pipeline (CUDA engine): pinned staging, one stream, one synchronisation per call
+        self._pipe = None
+        if device is not None and getattr(device, "type", "cpu") == "cuda" and hasattr(self.engine, "enqueue_forward"):
+            dd = dist if self.world > 1 else None
+            self._pipe = DevicePipeline(self.engine, dd, group)
+            self._stream = torch.cuda.ExternalStream(self.engine.stream(), device=device)
+            self._h_eps = torch.empty(LNT, dtype=torch.float64).pin_memory()
+            self._d_eps = torch.empty(LNT, dtype=torch.float64, device=device)
+            self._h_out = torch.empty(LNT + 3, dtype=torch.float64).pin_memory()
+            self._J_t = torch.as_tensor(_DevArray(self.engine.device_ptr(4), 3), device=device)
         self.J_parts = np.zeros(3)
         self.grad_J_Tb = np.zeros(LNT)
         self.grad_J_a = np.zeros(LNT)
@@ -51,6 +61,20 @@ class ShardedGrape:
 
     def evaluate_gradient(self, G, pulsevals):
         e = self.engine
+        if self._pipe is not None:
+            t = self._torch
+            LNT = G.shape[0]
+            self._h_eps.numpy()[:] = pulsevals
+            with t.cuda.stream(self._stream):
+                self._d_eps.copy_(self._h_eps, non_blocking=True)
+                self._pipe.step(self._d_eps)
+                self._h_out[:LNT].copy_(self._pipe.gradient(), non_blocking=True)
+                self._h_out[LNT:].copy_(self._J_t, non_blocking=True)
+            self._pipe.finish()          # one stream synchronisation + chi-norm / Taylor error flags
+            out = self._h_out.numpy()
+            G[:] = out[:LNT]
+            self.J_parts[:] = out[LNT:]
+            return float(np.sum(self.J_parts))
         sums = e.forward(pulsevals)
         sums_g = self._allreduce(self._sums, sums)
         self.J_parts[:] = e.backward(sums_g, self._G_partial)

@@ -189,7 +189,7 @@ int grape_b200_enqueue_combine(grape_b200_handle* h);
 int grape_b200_finish(grape_b200_handle* h);
 /* Device pointer of the handle's gradient buffer [L*NT] and sums buffer [4]
  * (for in-place collectives by the caller). */
-void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which); /* 0: grad_J_Tb (local partial), 1: sums[4], 2: pulsevals, 3: G */
+void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which); /* 0: grad_J_Tb (local partial), 1: sums[4], 2: pulsevals, 3: G, 4: J_parts[3], 5: tau[K] complex */
 /* cudaStream_t the handle launches on (so callers can time with events on it). */
 void* grape_b200_stream(grape_b200_handle* h);
 /* number of kernels launched by this handle since creation */

@@ -279,6 +279,7 @@ def main():
         t_e2e = float(t.item())
         e2e = dict(value=units_per_step / t_e2e, unit=UNIT, ms_per_step=t_e2e * 1e3,
                    h2d_bytes_per_step=8 * (LNT + 4), d2h_bytes_per_step=8 * (2 * LNT + 3 + 4 + 2 * local.K + 8))
+        sh.close()
 
     if rank != 0:
         if dist is not None:

@@ -52,6 +52,22 @@ class ShardedGrape:
         self.grad_J_a = np.zeros(LNT)
         self.K_local = self.local.K
 
+    def close(self):
+        """Releases the pinned staging buffers while the engine's stream is still alive: torch's
+        pinned-host allocator records an event on every stream a block was used on when the block
+        is freed, so they must go before `grape_b200_destroy` destroys that stream."""
+        if self._pipe is not None:
+            self.engine.finish()
+            self._h_eps = self._h_out = self._d_eps = self._J_t = None
+            self._pipe = None
+            self._stream = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def _allreduce(self, buf, host):
         t = self._torch
         buf.copy_(t.from_numpy(host))

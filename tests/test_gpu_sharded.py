@@ -23,6 +23,8 @@ def test_pipeline_matches_blocking_call(lib_built):
         G1 = np.zeros_like(eps)
         J1 = sh.evaluate_gradient(G1, eps)
         assert np.array_equal(G0, G1) and J0 == J1
+        sh.close()
+        e.close()
 
 
 def test_two_shards_on_one_device_sum_to_full_gradient(lib_built):

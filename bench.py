@@ -316,18 +316,29 @@ def main():
             pass
         if p.N > 32:
             # dense path: FP64 tensor-core (DMMA) roofline; peak measured on this GPU in this run
-            f_fwd, f_bwd, terms = pk.dense_flops_per_unit(p, eps)
-            share = {1: f_fwd, 3: f_bwd}.get(dom, 0.0)
+            form = eng.gradient_form()
+            f_fwd, f_bwd, f_con, terms = pk.dense_flops_per_unit(p, eps, form)
+            f_step = f_fwd + f_bwd + f_con
+            share = {1: f_fwd, 3: f_bwd, 4: f_con}.get(dom, 0.0)
+            kname = {1: "forward_sweep (dense_chain / dense2_chain, DMMA m8n8k4)",
+                     3: "backward_sweep (" + ("dense_chain / dense2_chain" if form else "dense_backward / dense2_backward")
+                        + ", DMMA m8n8k4)",
+                     4: "gradient_contraction (kry_contract, DMMA m8n8k4)"}.get(dom, names[dom])
             achieved = share * units_per_step / (k_ms * 1e-3) / 1e12
             line["roofline"] = dict(
-                bound="tensor", kernel=names[dom] + (" (dense2_backward / dense_backward, DMMA m8n8k4)" if dom == 3 else ""),
+                bound="tensor", kernel=kname,
                 achieved=achieved, peak=fp["dmma_tflops"], unit="TFLOP/s",
                 frac=achieved / fp["dmma_tflops"] if fp["dmma_tflops"] > 0 else None, traffic=traffic,
                 peak_source="FP64 DMMA peak measured on this GPU in this run (csrc/peaks.cu); MEASURED_PEAKS.json "
                             "carries no FP64 figure",
-                kernel_ms=k_ms, flops_per_unit_kernel=share, flops_per_unit_step=f_fwd + f_bwd, taylor_terms=terms,
-                step_tflops=(f_fwd + f_bwd) * units_per_step / (ms_per_step * 1e-3) / 1e12,
-                step_frac=(f_fwd + f_bwd) * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dmma_tflops"],
+                kernel_ms=k_ms, flops_per_unit_kernel=share, flops_per_unit_step=f_step, taylor_terms=terms,
+                gradient_form="krylov" if form else "block_recursion",
+                flops_per_unit_reference_count=8.0 * p.N * p.N * terms * (2 + 2 * p.L),
+                step_tflops=f_step * units_per_step / (ms_per_step * 1e-3) / 1e12,
+                step_frac=f_step * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dmma_tflops"],
+                phase_tflops={nm: (fl * units_per_step / (float(ph) * 1e-3) / 1e12 if ph > 0 else None)
+                              for nm, fl, ph in (("forward_sweep", f_fwd, phase[1]), ("backward_sweep", f_bwd, phase[3]),
+                                                 ("gradient_contraction", f_con, phase[4]))},
                 phase_ms=dict(zip(names, [float(v) for v in phase[:5]])),
                 share_of_step=k_ms / float(phase[6]) if phase[6] > 0 else None)
         else:

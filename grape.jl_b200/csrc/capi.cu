@@ -14,6 +14,7 @@
 #include "warp_seg.cuh"
 #include "dense.cuh"
 #include "dense2.cuh"
+#include "dense_kry.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -330,6 +331,7 @@ void run_forward(H* h, bool need_storage = true) {
             } else warp_run_forward(h->warp, h->p, h->stream, h->launches);
             break;
         case GRAPE_B200_PATH_DENSE:
+            kry_run_plan(h->dense, h->p, h->stream, h->launches);
             if (h->dense2.on) dense2_run_forward(h->dense2, h->dense, h->p, h->stream, h->launches);
             else dense_run_forward(h->dense, h->p, h->stream, h->launches);
             break;
@@ -372,7 +374,9 @@ void run_gradient(H* h) {
                            (small_gradient_t<3, 2>(h)), (small_gradient_t<4, 1>(h)));
             break;
         case GRAPE_B200_PATH_WARP: warp_run_gradient(h->warp, h->p, h->stream, h->launches); break;
-        case GRAPE_B200_PATH_DENSE: break;   // fused into dense_run_backward
+        case GRAPE_B200_PATH_DENSE:   // block recursion: fused into the backward sweep; Krylov form: contraction over all steps
+            kry_run_gradient(h->dense, h->p, h->stream, h->launches);
+            break;
     }
 }
 void run_finalize(H* h, bool grad) {
@@ -623,6 +627,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
             rc = dense_setup(h->dense, p, d, h->dev_allocs, e);
             if (!rc) rc = dense2_setup(h->dense2, h->dense, p, h->dev_allocs, e);
             if (!rc && !h->dense2.on && !h->dense.strip_ok) { e = h->dense.strip_err; rc = GRAPE_B200_EINVAL; }
+            if (!rc) rc = kry_setup(h->dense, h->dense2, p, h->dev_allocs, e);
             if (rc) h->err = e;
             break;
         }
@@ -940,5 +945,16 @@ void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which) {
 }
 void* grape_b200_stream(grape_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
 int64_t grape_b200_launch_count(const grape_b200_handle* h) { return h ? h->launches : 0; }
+int grape_b200_gradient_form(grape_b200_handle* h) {
+    if (!h) return -GRAPE_B200_EINVAL;
+    if (h->path != GRAPE_B200_PATH_DENSE || !h->dense.kd.on) return 0;
+    int ok = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
+        cudaMemcpy(&ok, h->dense.kd.ok, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        h->err = "CUDA error while reading the gradient form";
+        return -GRAPE_B200_ECUDA;
+    }
+    return ok ? 1 : 0;
+}
 
 }  // extern "C"

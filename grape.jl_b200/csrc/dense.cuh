@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -35,8 +36,30 @@ constexpr int DENSE_LMAX = 8;
 constexpr int DENSE_CGP = 4;      // column groups (of 8 columns) per DMMA pass
 constexpr int DENSE_THREADS = 256;
 
+constexpr int KRY_MTMAX = 20;   // compile-time cap of Taylor-term slots per step (Krylov-form backward)
+
+// Krylov-form backward (dense_kry.cuh): per step the Taylor terms of both sweeps are kept in HBM,
+//   bh_a = (-i H dt)^a Psi / a!   (forward chain),   ch_b = (+i H^dagger dt)^b chi / b!   (backward chain),
+// and the gradient of ALL controls comes from one contraction per step (no mu_l mat-vecs in the chain).
+struct KryDev {
+    int on;            // term storage allocated and the Krylov-form backward is available for this handle
+    int MT;            // term slots per step (<= KRY_MTMAX)
+    int TP, TT;        // 64x64 contraction tiles per dimension / per step
+    int KC;            // contraction chunk (8 or 16 columns of a term slot)
+    int* m_n;          // [NT] Taylor order of every step (kry_plan)
+    int* ok;           // [1] 1: every step has s == 0 and m <= MT -> Krylov-form kernels run, block recursion skips
+    int* kb;           // [1] number of partial-gradient slabs finalize_grad sums (1 on the Krylov path)
+    double* FT;        // [NT][MT][2][Np][Kp]  forward terms, overwritten by e_b = rho sum_a beta(a,b) bh_a
+    double* BT;        // [NT][MT][2][Np][Kp]  backward terms, slot 0 = chi(t_n)
+    double* kcur;      // [2][Np][Kp]  state of the backward chain
+    double* kcur2;     // ping-pong partner (tiled chain)
+    double* tilepart;  // [NT][TT][L]
+};
+
 struct DenseDev {
     int Np, Kp, Cb, RT, Pf, Pb, MS, CcapF, CcapB, nD;
+    const int* kry_ok; // block-recursion backward kernels return at once if *kry_ok (nullptr: always run)
+    unsigned* bar;     // [GBAR_WORDS] grid-barrier counters of the chain kernels (zeroed before each launch)
     int mu_smem;   // backward strip kernel keeps its 8 rows of every mu_l^dagger in shared memory
     const double* Hf;
     const double* Ha;
@@ -54,12 +77,14 @@ struct DenseDev {
 
 struct DensePlan {
     DenseDev d;
+    KryDev kd;
+    size_t kry_smem;
     int gridF, gridB;
     size_t smemF, smemB;
     bool ready;
     bool strip_ok;        // the 8-row strip kernels of this file can run (N, K(L+1) small enough)
     std::string strip_err;
-    DensePlan() : gridF(0), gridB(0), smemF(0), smemB(0), ready(false), strip_ok(true) {}
+    DensePlan() : kry_smem(0), gridF(0), gridB(0), smemF(0), smemB(0), ready(false), strip_ok(true) { memset(&kd, 0, sizeof kd); }
 };
 
 GB_D void dmma884(double (&acc)[2], double a, double b) {
@@ -75,32 +100,51 @@ struct DAcc {
 // Accumulates, for NG column groups, sum over this warp's k-slice of
 //   B[r][k] * X[k][c]   with B = 8 rows (stride bstride, scaled by bscale), X planar global (ld = ldx)
 // DMMA mapping: A[m][k] = X[k0+k][col0+m], B[k][n] = Brow[n][k0+k], D[m][n] = out[row n][col m].
-template <int NG, bool BSMEM>
+// The operand block X was written by other CTAs one grid barrier ago and comes from L2: the loads of UK
+// k-steps are issued back to back before the first DMMA so that their latency overlaps.
+template <int NG, bool BSMEM, int UK>
 GB_D void dense_mma_slice(const double* __restrict__ Bre, const double* __restrict__ Bim, int bstride,
                           double bscale, const double* __restrict__ Xre, const double* __restrict__ Xim,
                           int ldx, const int (&col0)[NG], int ng, int kbeg, int kend, DAcc (&acc)[NG]) {
     const int lane = threadIdx.x & 31;
     const int lr = lane >> 2, lc = lane & 3;
-#pragma unroll 4
-    for (int k0 = kbeg; k0 < kend; k0 += 4) {
-        double bre, bim;
-        if (BSMEM) {
-            bre = bscale * Bre[lr * bstride + k0 + lc];
-            bim = bscale * Bim[lr * bstride + k0 + lc];
-        } else {
-            bre = bscale * __ldg(&Bre[(size_t)lr * bstride + k0 + lc]);
-            bim = bscale * __ldg(&Bim[(size_t)lr * bstride + k0 + lc]);
+    for (int kb = kbeg; kb < kend; kb += 4 * UK) {
+        double are[UK][NG], aim[UK][NG];
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int k0 = kb + 4 * u;
+            if (k0 < kend) {
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (g < ng) {
+                        const size_t off = (size_t)(k0 + lc) * ldx + col0[g] + lr;
+                        are[u][g] = __ldcg(&Xre[off]);
+                        aim[u][g] = __ldcg(&Xim[off]);
+                    }
+                }
+            }
         }
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            if (g < ng) {
-                const size_t off = (size_t)(k0 + lc) * ldx + col0[g] + lr;
-                const double are = __ldcg(&Xre[off]);
-                const double aim = __ldcg(&Xim[off]);
-                dmma884(acc[g].p1, are, bre);
-                dmma884(acc[g].p2, aim, bim);
-                dmma884(acc[g].q1, are, bim);
-                dmma884(acc[g].q2, aim, bre);
+        for (int u = 0; u < UK; ++u) {
+            const int k0 = kb + 4 * u;
+            if (k0 < kend) {
+                double bre, bim;
+                if (BSMEM) {
+                    bre = bscale * Bre[lr * bstride + k0 + lc];
+                    bim = bscale * Bim[lr * bstride + k0 + lc];
+                } else {
+                    bre = bscale * __ldg(&Bre[(size_t)lr * bstride + k0 + lc]);
+                    bim = bscale * __ldg(&Bim[(size_t)lr * bstride + k0 + lc]);
+                }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    if (g < ng) {
+                        dmma884(acc[g].p1, are[u][g], bre);
+                        dmma884(acc[g].p2, aim[u][g], bim);
+                        dmma884(acc[g].q1, are[u][g], bim);
+                        dmma884(acc[g].q2, aim[u][g], bre);
+                    }
+                }
             }
         }
     }
@@ -168,10 +212,17 @@ GB_D void dense_form_H(const DevP& p, const double* __restrict__ Hall, int Np, i
 }
 
 // ---------------------------------------------------------------------------
-// Forward sweep (reference src/optimize.jl:720-751)
+// Chain kernel: forward sweep (BWD = false; reference src/optimize.jl:720-751) and the chi chain of the
+// Krylov-form backward (BWD = true; chi <- exp(+i H^dagger dt) chi going down in n, plus the running-cost
+// inhomogeneity of optimize.jl:897-908). Same Taylor recursion on a block of K states in both directions.
+// When the step qualifies for the Krylov form (s == 0, m <= MT) every Taylor term goes to its own HBM slot
+// (FT / BT) instead of the T0/T1 ping-pong, at no extra traffic.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_forward(DevP p, DenseDev d) {
-    cgx::grid_group grid = cgx::this_grid();
+template <bool BWD>
+__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev d, KryDev kd) {
+    if (BWD && !(*kd.ok)) return;   // uniform over the grid
+    GridBarrier grid;
+    grid.init(d.bar);
     extern __shared__ __align__(16) double dsm[];
     const int Np = d.Np, Kp = d.Kp, MS = d.MS, NT = p.NT;
     const int rt = blockIdx.x / d.Pf, part = blockIdx.x % d.Pf;
@@ -188,13 +239,23 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_forward(DevP p, DenseD
     const size_t splane = (size_t)Np * Kp;
     const int w = threadIdx.x >> 5;
     const int kslice = Np / 8, kbeg = w * kslice, kend = kbeg + kslice;
-    const bool gb = p.gb_kind != 0;
+    const bool gb = BWD ? (p.gb_kind != 0 && p.lambda_b != 0.0) : (p.gb_kind != 0);
     const size_t hplane = (size_t)Np * Np;
+    double* state = BWD ? kd.kcur : d.cur;
+    const double* Hall = BWD ? d.Ha : d.Hf;
+    double* terms = BWD ? kd.BT : kd.FT;
 
     for (int e = threadIdx.x; e < 8 * ncols; e += DENSE_THREADS) {
         const int r = e / ncols, c = e % ncols;
-        acc_re[r * Ccap + c] = d.cur[(size_t)(r0 + r) * Kp + cbeg + c];
-        acc_im[r * Ccap + c] = d.cur[splane + (size_t)(r0 + r) * Kp + cbeg + c];
+        const size_t off = (size_t)(r0 + r) * Kp + cbeg + c;
+        const double vr = state[off], vi = state[splane + off];
+        acc_re[r * Ccap + c] = vr;
+        acc_im[r * Ccap + c] = vi;
+        if (BWD) {   // slot 0 of the last step = chi(T)
+            double* s0 = terms + (size_t)(NT - 1) * kd.MT * 2 * splane;
+            s0[off] = vr;
+            s0[splane + off] = vi;
+        }
     }
     for (int c = threadIdx.x; c < Ccap; c += DENSE_THREADS) jb_s[c] = 0.0;
     __syncthreads();
@@ -208,8 +269,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_forward(DevP p, DenseD
 #pragma unroll
             for (int g = 0; g < DENSE_CGP; ++g) { col0[g] = (pg + g) * 8; acc[g].zero(); }
             // D is shared (nD == 1) on the dense path
-            dense_mma_slice<DENSE_CGP, false>(d.Dm + (size_t)r0 * Np, d.Dm + hplane + (size_t)r0 * Np, Np, 1.0,
-                                              d.cur, d.cur + splane, Kp, col0, ng, kbeg, kend, acc);
+            dense_mma_slice<DENSE_CGP, false, 2>(d.Dm + (size_t)r0 * Np, d.Dm + hplane + (size_t)r0 * Np, Np, 1.0,
+                                                 d.cur, d.cur + splane, Kp, col0, ng, kbeg, kend, acc);
             const cplx res = dense_reduce<DENSE_CGP>(red, acc, ng);
             const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
             // reuse `red` as scratch for the row reduction
@@ -230,37 +291,50 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_forward(DevP p, DenseD
         }
     };
 
-    for (int n = 0; n < NT; ++n) {
+    for (int it = 0; it < NT; ++it) {
+        const int n = BWD ? NT - 1 - it : it;
         const double dt = p.tlist[n + 1] - p.tlist[n];
-        if (gb) {
+        if (!BWD && gb) {
             const double wgt = n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]);
             gb_point(wgt);
         }
-        dense_form_H(p, d.Hf, Np, MS, r0, n, Hs_re, Hs_im);
+        dense_form_H(p, Hall, Np, MS, r0, n, Hs_re, Hs_im);
         int m, s;
         dense_plan(p, d, n, dt, m, s);
-        if (p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
+        if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
+        const bool kry = kd.on && s == 0 && m <= kd.MT;
+        double* slots = kry ? terms + (size_t)n * kd.MT * 2 * splane : nullptr;
         __syncthreads();
         const int nsub = 1 << s;
         const double dts = dt / nsub;
         for (int sub = 0; sub < nsub; ++sub) {
             for (int j = 1; j <= m; ++j) {
-                const double* src = j == 1 ? d.cur : ((j - 1) & 1 ? d.T1 : d.T0);
-                double* dst = (j & 1) ? d.T1 : d.T0;
+                const double* src = j == 1 ? state : (kry ? slots + (size_t)(j - 1) * 2 * splane : ((j - 1) & 1 ? d.T1 : d.T0));
+                double* dst = kry ? slots + (size_t)j * 2 * splane : ((j & 1) ? d.T1 : d.T0);
                 const double x = dts / j;
                 for (int pg = cg0; pg < cg1; pg += DENSE_CGP) {
                     const int ng = min(DENSE_CGP, cg1 - pg);
-                    int col0[DENSE_CGP];
-                    DAcc acc[DENSE_CGP];
+                    cplx res;
+                    if (ng == 1) {   // 8 columns per CTA (few trajectories): deeper load batches
+                        int col0[1] = {pg * 8};
+                        DAcc acc[1];
+                        acc[0].zero();
+                        dense_mma_slice<1, true, 16>(Hs_re, Hs_im, MS, 1.0, src, src + splane, Kp, col0, 1, kbeg, kend, acc);
+                        res = dense_reduce<1>(red, acc, 1);
+                    } else {
+                        int col0[DENSE_CGP];
+                        DAcc acc[DENSE_CGP];
 #pragma unroll
-                    for (int g = 0; g < DENSE_CGP; ++g) { col0[g] = (pg + g) * 8; acc[g].zero(); }
-                    dense_mma_slice<DENSE_CGP, true>(Hs_re, Hs_im, MS, 1.0, src, src + splane, Kp, col0, ng, kbeg, kend, acc);
-                    const cplx res = dense_reduce<DENSE_CGP>(red, acc, ng);
+                        for (int g = 0; g < DENSE_CGP; ++g) { col0[g] = (pg + g) * 8; acc[g].zero(); }
+                        dense_mma_slice<DENSE_CGP, true, 2>(Hs_re, Hs_im, MS, 1.0, src, src + splane, Kp, col0, ng, kbeg, kend, acc);
+                        res = dense_reduce<DENSE_CGP>(red, acc, ng);
+                    }
                     const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
                     if (g < ng) {
-                        // t = (-i x) * res
-                        const double tr = x * res.y, ti = -x * res.x;
+                        // forward: t = (-i x) * res ; backward: t = (+i x) * res
+                        const double tr = BWD ? -x * res.y : x * res.y;
+                        const double ti = BWD ? x * res.x : -x * res.x;
                         const int cglob = (pg + g) * 8 + mc;
                         if (j < m) {
                             dst[(size_t)(r0 + nrow) * Kp + cglob] = tr;
@@ -274,22 +348,53 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_forward(DevP p, DenseD
             }
             __syncthreads();
             const bool last = sub == nsub - 1;
+            if (BWD && last && gb && n > 0) {
+                // chi += lambda_b * 0.5 (t_{n+1} - t_{n-1}) / rho * xi(Psi(t_{n-1})), xi = -D Psi  (optimize.jl:897-908)
+                const double* st = d.store + (size_t)n * 2 * splane;
+                const double f = p.lambda_b * 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]);
+                for (int pg = cg0; pg < cg1; pg += DENSE_CGP) {
+                    const int ng = min(DENSE_CGP, cg1 - pg);
+                    int col0[DENSE_CGP];
+                    DAcc acc[DENSE_CGP];
+#pragma unroll
+                    for (int g = 0; g < DENSE_CGP; ++g) { col0[g] = (pg + g) * 8; acc[g].zero(); }
+                    dense_mma_slice<DENSE_CGP, false, 2>(d.Dm + (size_t)r0 * Np, d.Dm + hplane + (size_t)r0 * Np, Np, 1.0,
+                                                         st, st + splane, Kp, col0, ng, kbeg, kend, acc);
+                    const cplx res = dense_reduce<DENSE_CGP>(red, acc, ng);
+                    const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
+                    if (g < ng) {
+                        const int k = (pg + g) * 8 + mc;
+                        if (k < p.K) {
+                            const double fk = f / p.rho[k];
+                            acc_re[nrow * Ccap + k - cbeg] -= fk * res.x;
+                            acc_im[nrow * Ccap + k - cbeg] -= fk * res.y;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
             for (int e = threadIdx.x; e < 8 * ncols; e += DENSE_THREADS) {
                 const int r = e / ncols, c = e % ncols;
                 const size_t off = (size_t)(r0 + r) * Kp + cbeg + c;
                 const double vr = acc_re[r * Ccap + c], vi = acc_im[r * Ccap + c];
-                d.cur[off] = vr;
-                d.cur[splane + off] = vi;
+                state[off] = vr;
+                state[splane + off] = vi;
                 if (last) {
-                    double* st = d.store + (size_t)(n + 1) * 2 * splane;
-                    __stcs(&st[off], vr);
-                    __stcs(&st[splane + off], vi);
+                    if (!BWD) {
+                        double* st = d.store + (size_t)(n + 1) * 2 * splane;
+                        __stcs(&st[off], vr);
+                        __stcs(&st[splane + off], vi);
+                    } else if (n > 0) {   // slot 0 of the next (earlier) step = chi(t_{n-1})
+                        double* s0 = terms + (size_t)(n - 1) * kd.MT * 2 * splane;
+                        s0[off] = vr;
+                        s0[splane + off] = vi;
+                    }
                 }
             }
             grid.sync();
         }
     }
-    if (gb) {
+    if (!BWD && gb) {
         gb_point(0.5 * (p.tlist[NT] - p.tlist[NT - 1]));
         for (int c = threadIdx.x; c < ncols; c += DENSE_THREADS)
             d.jbpart[(size_t)blockIdx.x * Kp + cbeg + c] = jb_s[c];
@@ -301,6 +406,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_forward(DevP p, DenseD
 // (reference src/optimize.jl:880-911; GradGenerator block, docs/src/background.md:467-477)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, DenseDev d) {
+    if (d.kry_ok && *d.kry_ok) return;   // the Krylov-form kernels (dense_kry.cuh) serve this call; uniform over the grid
     cgx::grid_group grid = cgx::this_grid();
     extern __shared__ __align__(16) double dsm[];
     const int Np = d.Np, Kp = d.Kp, Cb = d.Cb, MS = d.MS, NT = p.NT, L = p.L;
@@ -356,7 +462,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
 #pragma unroll
                     for (int g = 0; g < DENSE_CGP; ++g) { col0[g] = (pg + g) * 8; acc[g].zero(); }
                     // H^dagger * [chi'_l .. chi]
-                    dense_mma_slice<DENSE_CGP, true>(Hs_re, Hs_im, MS, 1.0, src, src + bplane, Cb, col0, ng, kbeg, kend, acc);
+                    dense_mma_slice<DENSE_CGP, true, 4>(Hs_re, Hs_im, MS, 1.0, src, src + bplane, Cb, col0, ng, kbeg, kend, acc);
                     // + mu_l^dagger * chi  into the chi'_l columns
 #pragma unroll
                     for (int g = 0; g < DENSE_CGP; ++g) {
@@ -369,10 +475,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
                                 const double sl = p.shape ? p.shape[l * NT + n] : 1.0;
                                 if (d.mu_smem) {
                                     const double* Ml = Mu_s + (size_t)(l * 2) * 8 * MS;
-                                    dense_mma_slice<1, true>(Ml, Ml + 8 * MS, MS, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
+                                    dense_mma_slice<1, true, 8>(Ml, Ml + 8 * MS, MS, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
                                 } else {
                                     const double* Bl = d.Ha + (size_t)(1 + l) * 2 * hplane + (size_t)r0 * Np;
-                                    dense_mma_slice<1, false>(Bl, Bl + hplane, Np, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
+                                    dense_mma_slice<1, false, 8>(Bl, Bl + hplane, Np, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);
                                 }
                                 acc[g] = a1[0];
                             }
@@ -431,7 +537,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
                         DAcc acc[DENSE_CGP];
 #pragma unroll
                         for (int g = 0; g < DENSE_CGP; ++g) { col0[g] = (pg + g) * 8 - chi0; acc[g].zero(); }
-                        dense_mma_slice<DENSE_CGP, false>(d.Dm + (size_t)r0 * Np, d.Dm + hplane + (size_t)r0 * Np, Np, 1.0,
+                        dense_mma_slice<DENSE_CGP, false, 4>(d.Dm + (size_t)r0 * Np, d.Dm + hplane + (size_t)r0 * Np, Np, 1.0,
                                                           st, st + splane, Kp, col0, ng, kbeg, kend, acc);
                         const cplx res = dense_reduce<DENSE_CGP>(red, acc, ng);
                         const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
@@ -483,7 +589,7 @@ __global__ void __launch_bounds__(256) dense_tau(DevP p, DenseDev d, int gridF) 
 }
 
 // chi_k(T) boundary condition, normalisation, initial backward block  (optimize.jl:845-869, 878)
-__global__ void __launch_bounds__(256) dense_boundary(DevP p, DenseDev d, const cplx* __restrict__ chi_host) {
+__global__ void __launch_bounds__(256) dense_boundary(DevP p, DenseDev d, const cplx* __restrict__ chi_host, double* __restrict__ kcur) {
     __shared__ double s_buf[32];
     __shared__ double s_rho;
     const int k = blockIdx.x;
@@ -539,6 +645,10 @@ __global__ void __launch_bounds__(256) dense_boundary(DevP p, DenseDev d, const 
         const double xr = d.bcur[off] * ir, xi = d.bcur[bplane + off] * ir;
         d.bcur[off] = xr;
         d.bcur[bplane + off] = xi;
+        if (kcur) {   // K-column state of the Krylov-form backward chain
+            kcur[(size_t)i * Kp + k] = xr;
+            kcur[splane + (size_t)i * Kp + k] = xi;
+        }
         if (i < N) p.chiT[(size_t)k * N + i] = mk(xr, xi);
     }
 }
@@ -686,6 +796,11 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     if ((rc = ald(&d.T1, 2 * bplane))) return rc;
     if ((rc = ald(&d.store, (size_t)(NT + 1) * 2 * splane))) return rc;
     if ((rc = ald(&d.jbpart, (size_t)dp.gridF * Kp))) return rc;
+    {
+        double* q = nullptr;
+        if ((rc = ald(&q, GBAR_WORDS / 2))) return rc;
+        d.bar = reinterpret_cast<unsigned*>(q);
+    }
     p.KB = dp.gridB;
     if ((rc = ald(&p.partial, (size_t)dp.gridB * L * NT))) return rc;
     const size_t redB = (size_t)(DENSE_THREADS / 32) * DENSE_CGP * 128;
@@ -698,7 +813,8 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     }
     if (dp.smemF > 227 * 1024 || dp.smemB > 227 * 1024) { dp.strip_ok = false; dp.strip_err = "dense strip kernels: shared-memory tile does not fit (N or K*(L+1) too large)"; }
     if (dp.strip_ok) {
-        cudaError_t e = cudaFuncSetAttribute(dense_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        cudaError_t e = cudaFuncSetAttribute(dense_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemB);
         if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e); return GRAPE_B200_ECUDA; }
     }
@@ -715,8 +831,9 @@ inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int
     cudaMemcpyAsync(d.cur, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(d.store, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     DevP pp = p;
-    void* args[] = {&pp, &d};
-    cudaLaunchCooperativeKernel((void*)dense_forward, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF, st);
+    void* args[] = {&pp, &d, &dp.kd};
+    cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
+    cudaLaunchCooperativeKernel((void*)dense_chain<false>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF, st);
     dense_tau<<<p.K, 256, 0, st>>>(p, d, dp.gridF);
     launches += 2;
 }
@@ -724,11 +841,17 @@ inline void dense_run_backward(DensePlan& dp, const DevP& p, const cplx* chi_hos
     DenseDev& d = dp.d;
     const size_t bplane = (size_t)d.Np * d.Cb;
     cudaMemsetAsync(d.bcur, 0, 2 * bplane * sizeof(double), st);
-    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host);
+    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host, dp.kd.on ? dp.kd.kcur : nullptr);
     DevP pp = p;
     void* args[] = {&pp, &d};
     cudaLaunchCooperativeKernel((void*)dense_backward, dim3(dp.gridB), dim3(DENSE_THREADS), args, dp.smemB, st);
     launches += 2;
+    if (dp.kd.on) {
+        void* cargs[] = {&pp, &d, &dp.kd};
+        cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
+        cudaLaunchCooperativeKernel((void*)dense_chain<true>, dim3(dp.gridF), dim3(DENSE_THREADS), cargs, dp.smemF, st);
+        launches += 1;
+    }
 }
 inline void dense_gather_final(DensePlan& dp, const DevP& p, cplx* out, cudaStream_t st, int64_t& launches) {
     const int cnt = p.K * p.N;

@@ -162,10 +162,14 @@ GB_D void d2_form(const DevP& p, const double* __restrict__ Mall, double* __rest
 }
 
 // ---------------------------------------------------------------------------
-// forward sweep (reference src/optimize.jl:720-751)
+// chain kernel: forward sweep (BWD = false; reference src/optimize.jl:720-751) or the chi chain of the
+// Krylov-form backward (BWD = true; see dense_chain in dense.cuh)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev d, Dense2Dev d2) {
-    cgx::grid_group grid = cgx::this_grid();
+template <bool BWD>
+__global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d, Dense2Dev d2, KryDev kd) {
+    if (BWD && !(*kd.ok)) return;   // uniform over the grid
+    GridBarrier grid;
+    grid.init(d.bar);
     extern __shared__ __align__(16) double dsm[];
     __shared__ double s_gb[4][D2_TN];
     const int Np = d.Np, Kp = d.Kp, NT = p.NT;
@@ -173,10 +177,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int lr = lane >> 2, lc = lane & 3, wr = w >> 1, wc = w & 1;
     const int NkF = Np / D2_KC_F;
-    const bool gb = p.gb_kind != 0;
+    const bool gb = BWD ? (p.gb_kind != 0 && p.lambda_b != 0.0) : (p.gb_kind != 0);
     const double one[1] = {1.0};
-    double* cur = d.cur;
-    double* nxt = d2.cur2;
+    double* cur = BWD ? kd.kcur : d.cur;
+    double* nxt = BWD ? kd.kcur2 : d2.cur2;
+    double* const cur_first = cur;
+    const double* Hall = BWD ? d.Ha : d.Hf;
+    double* terms = BWD ? kd.BT : kd.FT;
 
     // J_b contribution of the state in `cur` with weight wgt: Re <psi|D|psi> per trajectory
     auto gb_point = [&](double wgt) {
@@ -210,31 +217,44 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev
         }
     };
 
-    d2_form(p, d.Hf, d2.Hn[0], hplane, 0);
+    const int nfirst = BWD ? NT - 1 : 0;
+    d2_form(p, Hall, d2.Hn[nfirst & 1], hplane, nfirst);
+    if (BWD) {   // slot 0 of the last step = chi(T)
+        double* s0 = terms + (size_t)(NT - 1) * kd.MT * 2 * splane;
+        for (size_t e = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e < 2 * splane; e += (size_t)gridDim.x * D2_THREADS)
+            s0[e] = cur[e];
+    }
     grid.sync();
-    for (int n = 0; n < NT; ++n) {
+    for (int it = 0; it < NT; ++it) {
+        const int n = BWD ? NT - 1 - it : it;
+        const int nnext = BWD ? n - 1 : n + 1;
+        const bool has_next = BWD ? n > 0 : n + 1 < NT;
         const double dt = p.tlist[n + 1] - p.tlist[n];
         const double* Hn = d2.Hn[n & 1];
-        if (gb) gb_point(n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]));
+        if (!BWD && gb) gb_point(n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]));
         int m, s;
         dense_plan(p, d, n, dt, m, s);
-        if (p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
+        if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
+        const bool kry = kd.on && s == 0 && m <= kd.MT;
+        double* slots = kry ? terms + (size_t)n * kd.MT * 2 * splane : nullptr;
         const int nsub = 1 << s;
         const double dts = dt / nsub;
         for (int sub = 0; sub < nsub; ++sub) {
             const bool last = sub == nsub - 1;
             for (int j = 1; j <= m; ++j) {
-                const double* src = j == 1 ? cur : ((j - 1) & 1 ? d.T1 : d.T0);
-                double* dst = (j & 1) ? d.T1 : d.T0;
+                const double* src = j == 1 ? cur : (kry ? slots + (size_t)(j - 1) * 2 * splane : ((j - 1) & 1 ? d.T1 : d.T0));
+                double* dst = kry ? slots + (size_t)j * 2 * splane : ((j & 1) ? d.T1 : d.T0);
                 const double x = dts / j;
-                if (j == m && last && n + 1 < NT) d2_form(p, d.Hf, d2.Hn[(n + 1) & 1], hplane, n + 1);
+                const bool fin = j == m && last;
+                if (fin && has_next) d2_form(p, Hall, d2.Hn[nnext & 1], hplane, nnext);
                 for (int t = blockIdx.x; t < d2.ntiles; t += gridDim.x) {
                     const int r0 = (t / d2.tilesC) * D2_TM, c0 = (t % d2.tilesC) * D2_TN;
                     const double* A[1] = {Hn + (size_t)r0 * Np};
                     const double* B[1] = {src + c0};
                     const int row = r0 + wr * 8 + lr;
-                    const size_t off = (size_t)row * Kp + c0 + wc * 8 + 2 * lc;
+                    const int kc = c0 + wc * 8 + 2 * lc;
+                    const size_t off = (size_t)row * Kp + kc;
                     const double* base = j == 1 ? cur : nxt;
                     // running sum of this thread's elements: loaded before the GEMM so that the latency is hidden
                     const double2 b_r = *reinterpret_cast<const double2*>(&base[off]);
@@ -243,9 +263,9 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev
                     d2_tile_gemm<1, false, D2_KC_F>(dsm, A, hplane, Np, B, splane, Kp, NkF, one, acc);
                     double tr[2], ti[2], vr[2], vi[2];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {   // t = (-i x) * res
-                        tr[e] = x * acc[0].im[e];
-                        ti[e] = -x * acc[0].re[e];
+                    for (int e = 0; e < 2; ++e) {   // forward: t = (-i x) * res ; backward: t = (+i x) * res
+                        tr[e] = BWD ? -x * acc[0].im[e] : x * acc[0].im[e];
+                        ti[e] = BWD ? x * acc[0].re[e] : -x * acc[0].re[e];
                     }
                     vr[0] = b_r.x + tr[0]; vr[1] = b_r.y + tr[1];
                     vi[0] = b_i.x + ti[0]; vi[1] = b_i.y + ti[1];
@@ -253,12 +273,36 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev
                         *reinterpret_cast<double2*>(&dst[off]) = make_double2(tr[0], tr[1]);
                         *reinterpret_cast<double2*>(&dst[splane + off]) = make_double2(ti[0], ti[1]);
                     }
+                    if (BWD && fin && gb && n > 0) {
+                        // chi += lambda_b * 0.5 (t_{n+1} - t_{n-1}) / rho * xi(Psi(t_{n-1})), xi = -D Psi  (optimize.jl:897-908)
+                        const double f = p.lambda_b * 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]);
+                        const double* st = d.store + (size_t)n * 2 * splane;
+                        const double* A1[1] = {d.Dm + (size_t)r0 * Np};
+                        const double* B1[1] = {st + c0};
+                        D2Acc a1[1];
+                        d2_tile_gemm<1, false, D2_KC_F>(dsm, A1, hplane, Np, B1, splane, Kp, NkF, one, a1);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = kc + e;
+                            if (k < p.K) {
+                                const double fk = f / p.rho[k];
+                                vr[e] -= fk * a1[0].re[e];
+                                vi[e] -= fk * a1[0].im[e];
+                            }
+                        }
+                    }
                     *reinterpret_cast<double2*>(&nxt[off]) = make_double2(vr[0], vr[1]);
                     *reinterpret_cast<double2*>(&nxt[splane + off]) = make_double2(vi[0], vi[1]);
-                    if (j == m && last) {
-                        double* st = d.store + (size_t)(n + 1) * 2 * splane;
-                        __stcs(reinterpret_cast<double2*>(&st[off]), make_double2(vr[0], vr[1]));
-                        __stcs(reinterpret_cast<double2*>(&st[splane + off]), make_double2(vi[0], vi[1]));
+                    if (fin) {
+                        if (!BWD) {
+                            double* st = d.store + (size_t)(n + 1) * 2 * splane;
+                            __stcs(reinterpret_cast<double2*>(&st[off]), make_double2(vr[0], vr[1]));
+                            __stcs(reinterpret_cast<double2*>(&st[splane + off]), make_double2(vi[0], vi[1]));
+                        } else if (n > 0) {   // slot 0 of the next (earlier) step = chi(t_{n-1})
+                            double* s0 = terms + (size_t)(n - 1) * kd.MT * 2 * splane;
+                            *reinterpret_cast<double2*>(&s0[off]) = make_double2(vr[0], vr[1]);
+                            *reinterpret_cast<double2*>(&s0[splane + off]) = make_double2(vi[0], vi[1]);
+                        }
                     }
                 }
                 grid.sync();
@@ -266,11 +310,13 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev
             double* tmp = cur; cur = nxt; nxt = tmp;
         }
     }
-    if (gb) gb_point(0.5 * (p.tlist[NT] - p.tlist[NT - 1]));
-    // final state must be in d.cur (read by dense_tau / dense_boundary / read-backs)
-    if (cur != d.cur) {
-        for (size_t e = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e < 2 * splane; e += (size_t)gridDim.x * D2_THREADS)
-            d.cur[e] = cur[e];
+    if (!BWD) {
+        if (gb) gb_point(0.5 * (p.tlist[NT] - p.tlist[NT - 1]));
+        // final state must be in d.cur (read by dense_tau / dense_boundary / read-backs)
+        if (cur != cur_first) {
+            for (size_t e = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e < 2 * splane; e += (size_t)gridDim.x * D2_THREADS)
+                cur_first[e] = cur[e];
+        }
     }
 }
 
@@ -280,6 +326,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_forward(DevP p, DenseDev
 template <int LB>
 __global__ void __launch_bounds__(D2_THREADS, 1) dense2_backward(DevP p, DenseDev d, Dense2Dev d2) {
     constexpr int L = LB - 1;
+    if (d.kry_ok && *d.kry_ok) return;   // the Krylov-form kernels (dense_kry.cuh) serve this call; uniform over the grid
     cgx::grid_group grid = cgx::this_grid();
     extern __shared__ __align__(16) double dsm[];
     __shared__ double s_buf[32 * (L > 0 ? L : 1)];
@@ -446,7 +493,8 @@ inline int dense2_setup(Dense2Plan& q, DensePlan& dp, DevP& p, std::vector<void*
     q.smemF = sizeof(double) * d2_stage_doubles(1, D2_KC_F) * D2_ST;
     q.smemB = std::max(sizeof(double) * d2_stage_doubles(LB, D2_KC_B) * D2_ST, q.smemF);
     if (q.smemB > 200 * 1024) return 0;
-    cudaError_t e = cudaFuncSetAttribute(dense2_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smemF);
+    cudaError_t e = cudaFuncSetAttribute(dense2_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smemF);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dense2_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smemF);
     if (e == cudaSuccess) {
         switch (LB) {
             case 2: e = dense2_attr_b<2>(q.smemB); break;
@@ -497,8 +545,9 @@ inline void dense2_run_forward(Dense2Plan& q, DensePlan& dp, const DevP& p, cuda
     cudaMemcpyAsync(d.store, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     if (p.gb_kind) cudaMemsetAsync(d.jbpart, 0, (size_t)q.d2.tilesR * d.Kp * sizeof(double), st);
     DevP pp = p;
-    void* args[] = {&pp, &d, &q.d2};
-    cudaLaunchCooperativeKernel((void*)dense2_forward, dim3(q.grid), dim3(D2_THREADS), args, q.smemF, st);
+    void* args[] = {&pp, &d, &q.d2, &dp.kd};
+    cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
+    cudaLaunchCooperativeKernel((void*)dense2_chain<false>, dim3(q.grid), dim3(D2_THREADS), args, q.smemF, st);
     dense_tau<<<p.K, 256, 0, st>>>(p, d, q.d2.tilesR);
     launches += 2;
 }
@@ -507,7 +556,7 @@ inline void dense2_run_backward(Dense2Plan& q, DensePlan& dp, const DevP& p, con
     DenseDev& d = dp.d;
     const size_t bplane = (size_t)d.Np * d.Cb;
     cudaMemsetAsync(d.bcur, 0, 2 * bplane * sizeof(double), st);
-    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host);
+    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host, dp.kd.on ? dp.kd.kcur : nullptr);
     DevP pp = p;
     void* args[] = {&pp, &d, &q.d2};
     void* fn = nullptr;
@@ -519,4 +568,10 @@ inline void dense2_run_backward(Dense2Plan& q, DensePlan& dp, const DevP& p, con
     }
     cudaLaunchCooperativeKernel(fn, dim3(q.grid), dim3(D2_THREADS), args, q.smemB, st);
     launches += 2;
+    if (dp.kd.on) {
+        void* cargs[] = {&pp, &d, &q.d2, &dp.kd};
+        cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
+        cudaLaunchCooperativeKernel((void*)dense2_chain<true>, dim3(q.grid), dim3(D2_THREADS), cargs, q.smemF, st);
+        launches += 1;
+    }
 }

@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(256) finalize_J(DevP p) {
 // grad_J_a[idx]  = 2 eps dt (fluence) ; G = grad_J_Tb + lambda_a grad_J_a  (optimize.jl:1003-1011)
 __global__ void __launch_bounds__(256) finalize_grad(DevP p) {
     const int LNT = p.L * p.NT;
+    const int KB = p.KBdev ? *p.KBdev : p.KB;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < LNT; idx += gridDim.x * blockDim.x) {
         double s = 0.0;
-        for (int kb = 0; kb < p.KB; ++kb) s += p.partial[(size_t)kb * LNT + idx];
+        for (int kb = 0; kb < KB; ++kb) s += p.partial[(size_t)kb * LNT + idx];
         const double gT = -2.0 * s;
         double ga = 0.0;
         if (p.ja_kind == 1) {

@@ -179,6 +179,13 @@ class GrapeEngine:
     def launch_count(self):
         return int(self.lib.grape_b200_launch_count(self._h))
 
+    def gradient_form(self):
+        """0: GradGenerator block recursion, 1: Krylov form (dense path) served the last gradient call."""
+        rc = int(self.lib.grape_b200_gradient_form(self._h))
+        if rc < 0:
+            self._check(-rc)
+        return rc
+
     def eval_fg_device(self, d_pulsevals_ptr, d_G_ptr=None, d_J_ptr=None):
         self._check(self.lib.grape_b200_eval_fg_device(self._h, d_pulsevals_ptr, d_G_ptr, d_J_ptr))
 

@@ -83,10 +83,13 @@ def executed_flops_per_unit(p, eps, sample=64):
     return float(a_flops + b_flops + c_flops)
 
 
-def dense_flops_per_unit(p, eps):
-    """Flops per unit of the dense (polynomial-apply) path, split (forward, backward):
-    8 N^2 m per state column and Taylor term; backward has (1 + 2L) columns per trajectory
-    (H^dagger on L+1 blocks, mu_l^dagger on chi); + one D Psi product per step each way with g_b.
+def dense_flops_per_unit(p, eps, form=0):
+    """Executed flops per unit of the dense (polynomial-apply) path as (forward, backward sweep, contraction, terms):
+    8 N^2 m per state column and Taylor term; + one D Psi product per step each way with g_b.
+    form 0, GradGenerator block recursion: the backward sweep has (1 + 2L) operator applications per trajectory
+    and term (H^dagger on L+1 blocks, mu_l^dagger on chi) and contains the contraction.
+    form 1, Krylov form (csrc/dense_kry.cuh): the backward chain has one column per trajectory, and the
+    contraction M_n = sum_{b,k} e_bk ch_bk^dagger costs 8 N^2 m per trajectory-step for all controls together.
     m follows dense_plan() (spectral-norm bound * 1.05)."""
     N, L, NT = p.N, p.L, p.NT
     e = np.abs(np.asarray(eps).reshape(L, NT))
@@ -98,5 +101,6 @@ def dense_flops_per_unit(p, eps):
     terms = float(np.mean(m * 2.0 ** sv))
     gbf = 8.0 * N * N if p.gb_kind else 0.0
     fwd = 8.0 * N * N * terms + gbf
-    bwd = 8.0 * N * N * terms * (1 + 2 * L) + gbf
-    return fwd, bwd, terms
+    if form == 1:
+        return fwd, 8.0 * N * N * terms + gbf, 8.0 * N * N * float(np.mean(m)), terms
+    return fwd, 8.0 * N * N * terms * (1 + 2 * L) + gbf, 0.0, terms

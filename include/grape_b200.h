@@ -194,6 +194,13 @@ void* grape_b200_device_ptr(grape_b200_handle* h, int32_t which); /* 0: grad_J_T
 void* grape_b200_stream(grape_b200_handle* h);
 /* number of kernels launched by this handle since creation */
 int64_t grape_b200_launch_count(const grape_b200_handle* h);
+/* Which backward kernels served the last gradient call (instrumentation; synchronises the stream):
+ *   0 = GradGenerator block recursion (1+2L operator applications per Taylor order; the only form
+ *       of the small / sub-warp paths' :taylor method, of sub-stepped steps and of gradient_method=:taylor),
+ *   1 = Krylov form (dense path: chi chain on K columns + one DMMA contraction per step, csrc/dense_kry.cuh).
+ * Both evaluate the same truncated series of the reference's GradGenerator step
+ * (src/optimize.jl:880-896, docs/src/background.md:447-494). Negative: error code. */
+int grape_b200_gradient_form(grape_b200_handle* h);
 
 #ifdef __cplusplus
 }

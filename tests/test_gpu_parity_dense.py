@@ -1,4 +1,5 @@
-"""GPU parity: dense DMMA path (N > 32, or forced) vs the CPU oracle, through the C-ABI."""
+"""GPU parity: dense DMMA path (N > 32, or forced) vs the CPU oracle, through the C-ABI.
+The case matrix over both backward forms lives in tests/test_gpu_parity_dense_krylov.py."""
 import numpy as np
 import pytest
 
@@ -10,37 +11,10 @@ from tests.test_gpu_parity_small import check, engine
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("N,K", [(33, 3), (40, 8), (64, 5), (100, 16), (130, 9)])
-def test_dense_random(lib_built, N, K):
-    p, eps = configs.c4_dense450(N=N, K=K, NT=6)
-    check(p, eps)
-
-
-@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
-def test_dense_functionals_nonhermitian_shaped(lib_built, functional):
-    N, K = 36, 5
-    p, eps = configs.random_problem(K=K, N=N, L=3, NT=5, G=1, seed=70 + functional, hermitian=False, shaped=True,
-                                    weights=np.linspace(0.5, 1.5, K), functional=functional)
-    p.tlist = p.tlist * (0.5 / np.sqrt(N))
-    check(p, eps)
-
-
 def test_dense_forced_on_small_problem(lib_built):
     p, eps = configs.random_problem(K=4, N=6, L=2, NT=8, G=1, seed=81, path=gb.PATH_DENSE)
     p.tlist = p.tlist * 0.5
     check(p, eps)
-
-
-def test_dense_large_norm_substeps(lib_built):
-    p, eps = configs.c4_dense450(N=48, K=4, NT=4)
-    p.tlist = p.tlist * 8.0      # ||H dt|| ~ 4: sub-steps
-    check(p, eps, rtol=1e-9)
-
-
-def test_dense_running_costs(lib_built):
-    p, eps = configs.c5_dense1024(N=40, K=6, NT=7)
-    e, ref = check(p, eps)
-    assert e.J_parts[1] > 0 and e.J_parts[2] > 0
 
 
 def test_dense_readbacks_and_split(lib_built):
@@ -56,12 +30,6 @@ def test_dense_readbacks_and_split(lib_built):
     Gp = np.zeros_like(eps)
     e.backward(sums, Gp)
     assert np.array_equal(Gp, G)
-
-
-def test_c4_reduced_steps_full_width(lib_built):
-    """C4 at full width (N=450, K=16) on 3 time steps: oracle parity."""
-    p, eps = configs.c4_dense450(NT=3)
-    check(p, eps)
 
 
 def test_c5_reduced_steps_full_width(lib_built):
@@ -88,22 +56,6 @@ def dense2_forced():
         del os.environ["GRAPE_B200_DENSE2"]
     else:
         os.environ["GRAPE_B200_DENSE2"] = old
-
-
-@pytest.mark.parametrize("N,K", [(33, 9), (64, 16), (100, 12), (130, 27), (40, 32)])
-def test_dense2_random(lib_built, dense2_forced, N, K):
-    p, eps = configs.c4_dense450(N=N, K=K, NT=5)
-    check(p, eps)
-
-
-@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
-@pytest.mark.parametrize("L", [1, 3, 4])
-def test_dense2_functionals_nonhermitian_shaped(lib_built, dense2_forced, functional, L):
-    N, K = 36, 11
-    p, eps = configs.random_problem(K=K, N=N, L=L, NT=5, G=1, seed=170 + functional + 10 * L, hermitian=False,
-                                    shaped=True, weights=np.linspace(0.5, 1.5, K), functional=functional)
-    p.tlist = p.tlist * (0.5 / np.sqrt(N))
-    check(p, eps)
 
 
 def test_dense2_substeps_and_running_costs(lib_built, dense2_forced):

@@ -1,0 +1,188 @@
+"""GPU parity of the two backward forms of the dense path against the CPU oracle and against each other.
+
+Krylov form (csrc/dense_kry.cuh; default when no step needs sub-stepping): chi chain on K columns, Taylor
+terms of both sweeps kept in HBM, one DMMA contraction per time step for all controls.
+Block recursion (csrc/dense.cuh, dense2.cuh; GRAPE_B200_KRYLOV=0, sub-stepped steps, :taylor): the
+GradGenerator block vector of the reference (src/optimize.jl:880-911) propagated term by term.
+Tolerance 1e-10 relative on J and every gradient element (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import grape.jl_b200 as gb
+from grape.jl_b200 import configs
+from oracle import grape_oracle as go
+from tests.test_gpu_parity_small import check, engine
+
+pytestmark = pytest.mark.gpu
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv = {k: str(v) for k, v in kv.items()}
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _both_forms(p, eps, rtol=1e-10, **env):
+    """oracle parity (J, J_parts, tau, G, grad_J_Tb, grad_J_a, evaluate_functional) with the Krylov form on
+    (default) and off; the two gradients agree to 1e-11. Returns them."""
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    scale = max(np.max(np.abs(ref["G"])), 1e-6)
+    out = []
+    for kry, form in ((1, 1), (0, 0)):
+        with _Env(GRAPE_B200_KRYLOV=kry, **env):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        J = e.evaluate_gradient(G, eps)
+        assert e.gradient_form() == form, (kry, e.gradient_form())
+        assert abs(J - ref["J"]) <= rtol * max(1.0, abs(ref["J"])), (J, ref["J"])
+        assert np.max(np.abs(e.J_parts - ref["J_parts"])) <= rtol * max(1.0, np.max(np.abs(ref["J_parts"])))
+        assert np.max(np.abs(e.tau_vals - ref["tau"])) <= rtol
+        err = np.max(np.abs(G - ref["G"])) / scale
+        assert err <= rtol, f"gradient rel err {err:.3e} (krylov={kry})"
+        assert np.max(np.abs(e.grad_J_Tb - ref["grad_J_Tb"])) / scale <= rtol
+        assert np.max(np.abs(e.grad_J_a - ref["grad_J_a"])) <= rtol * max(1.0, np.max(np.abs(ref["grad_J_a"])))
+        assert abs(e.evaluate_functional(eps) - ref["J"]) <= rtol * max(1.0, abs(ref["J"]))
+        out.append(G)
+        e.close()
+    assert np.max(np.abs(out[0] - out[1])) <= 1e-11 * scale
+    return out
+
+
+@pytest.mark.parametrize("N,K", [(33, 3), (40, 8), (64, 5), (100, 16), (130, 9), (65, 17)])
+def test_strip_kernels_both_forms(lib_built, N, K):
+    p, eps = configs.c4_dense450(N=N, K=K, NT=6)
+    _both_forms(p, eps, GRAPE_B200_DENSE2=0)
+
+
+@pytest.mark.parametrize("N,K", [(33, 9), (64, 16), (100, 12), (130, 27), (40, 32)])
+def test_tiled_kernels_both_forms(lib_built, N, K):
+    p, eps = configs.c4_dense450(N=N, K=K, NT=5)
+    _both_forms(p, eps, GRAPE_B200_DENSE2=1)
+
+
+@pytest.mark.parametrize("dense2", [0, 1])
+@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
+@pytest.mark.parametrize("L", [1, 3, 4])
+def test_nonhermitian_shaped_weighted(lib_built, dense2, functional, L):
+    N, K = 36, 11
+    p, eps = configs.random_problem(K=K, N=N, L=L, NT=5, G=1, seed=270 + functional + 10 * L, hermitian=False,
+                                    shaped=True, weights=np.linspace(0.5, 1.5, K), functional=functional)
+    p.tlist = p.tlist * (0.5 / np.sqrt(N))
+    _both_forms(p, eps, GRAPE_B200_DENSE2=dense2)
+
+
+@pytest.mark.parametrize("dense2", [0, 1])
+def test_running_costs_both_forms(lib_built, dense2):
+    """state running cost g_b = <Psi|D|Psi> (chi inhomogeneity in the chain, optimize.jl:897-908) + fluence J_a"""
+    p, eps = configs.c5_dense1024(N=40, K=16, NT=7)
+    _both_forms(p, eps, GRAPE_B200_DENSE2=dense2)
+    # non-uniform time grid: trapezoid weights and Taylor orders differ per step
+    p, eps = configs.c5_dense1024(N=48, K=8, NT=6)
+    p.tlist = np.cumsum(np.concatenate([[0.0], 0.25 * (1.0 + 0.4 * np.sin(1.0 + np.arange(p.NT)))]))
+    _both_forms(p, eps, GRAPE_B200_DENSE2=dense2)
+
+
+@pytest.mark.parametrize("dense2", [0, 1])
+def test_substeps_fall_back_to_block_recursion(lib_built, dense2):
+    """||H dt|| ~ 4 needs sub-steps: the device-side plan selects the block recursion for the call"""
+    p, eps = configs.c4_dense450(N=48, K=8, NT=4)
+    p.tlist = p.tlist * 8.0
+    with _Env(GRAPE_B200_DENSE2=dense2):
+        e, ref = check(p, eps, rtol=1e-9)
+    assert e.gradient_form() == 0
+    e.close()
+
+
+def test_form_switches_per_call_on_one_handle(lib_built):
+    """one handle, pulse vectors with ||H dt|| <= 1 on every step (Krylov form) and > 1 on some steps (block
+    recursion), alternating: the device-side plan picks the kernels per call and both match the oracle"""
+    p, eps = configs.c4_dense450(N=48, K=8, NT=5)
+    p.tlist = p.tlist * 2.5
+    e = engine(p)
+    op = go.from_problem(p)
+    for scale, form in ((0.1, 1), (1.0, 0), (0.1, 1), (1.0, 0)):
+        x = eps * scale
+        ref = go.evaluate_gradient(op, x)
+        G = np.zeros_like(x)
+        J = e.evaluate_gradient(G, x)
+        assert e.gradient_form() == form
+        assert abs(J - ref["J"]) <= 1e-9
+        assert np.max(np.abs(G - ref["G"])) <= 1e-9 * max(np.max(np.abs(ref["G"])), 1e-6)
+    e.close()
+
+
+def test_few_term_slots_fall_back(lib_built):
+    """GRAPE_B200_KRY_MT smaller than the Taylor order of the steps -> block recursion, same numbers"""
+    p, eps = configs.c4_dense450(N=40, K=8, NT=4)
+    with _Env(GRAPE_B200_KRY_MT=6):
+        e, ref = check(p, eps)
+        assert e.gradient_form() == 0
+    e.close()
+
+
+def test_taylor_method_uses_block_recursion(lib_built):
+    p, eps = configs.c4_dense450(N=40, K=8, NT=4, gradient_method=gb.TAYLOR)
+    e, ref = check(p, eps)
+    assert e.gradient_form() == 0
+    e.close()
+
+
+def test_split_forward_backward_and_host_chi(lib_built):
+    """sharded-style split call and the host-functional round trip go through the Krylov form too"""
+    p, eps = configs.c4_dense450(N=50, K=7, NT=5)
+    e, ref = check(p, eps)
+    G = np.zeros_like(eps)
+    e.evaluate_gradient(G, eps)
+    sums = e.forward(eps)
+    Gp = np.zeros_like(eps)
+    e.backward(sums, Gp)
+    assert e.gradient_form() == 1
+    assert np.array_equal(Gp, G)
+    e.close()
+    ph, _ = configs.c4_dense450(N=50, K=7, NT=5)
+    ph.functional = gb.HOST
+    eh = engine(ph)
+    eh.forward(eps)
+    psiT = eh.final_states()
+    tau = np.sum(np.conj(ph.tgt) * psiT, axis=1)
+    chiT = (np.sum(tau) / ph.K ** 2) * ph.tgt          # chi of J_T_sm, evaluated on the host
+    Gh = np.zeros_like(eps)
+    eh.backward_chi(chiT, Gh)
+    assert eh.gradient_form() == 1
+    assert np.max(np.abs(Gh - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
+    eh.close()
+
+
+def test_c4_full_width_forms_agree(lib_built):
+    """C4 at full width (N=450, K=16), 3 steps: oracle parity of the Krylov form, block recursion within 1e-11"""
+    p, eps = configs.c4_dense450(NT=3)
+    _both_forms(p, eps)
+
+
+def test_c5_full_width_forms_agree(lib_built):
+    """C5 at full width (N=1024, K=64, J_a + g_b), 2 steps: Krylov form vs block recursion (the dense Pade oracle
+    of a 3072 x 3072 block matrix per trajectory-step is too slow for 64 trajectories)"""
+    p, eps = configs.c5_dense1024(NT=2)
+    res = []
+    for kry in (1, 0):
+        with _Env(GRAPE_B200_KRYLOV=kry):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        J = e.evaluate_gradient(G, eps)
+        assert e.gradient_form() == kry
+        res.append((J, G))
+        e.close()
+    assert abs(res[0][0] - res[1][0]) <= 1e-12
+    assert np.max(np.abs(res[0][1] - res[1][1])) <= 1e-11 * np.max(np.abs(res[1][1]))

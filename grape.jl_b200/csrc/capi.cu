@@ -16,6 +16,7 @@
 #include "dense2.cuh"
 #include "dense_kry.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -178,12 +179,37 @@ int small_setup(H* h, const grape_b200_problem* d) {
     h->seg_on = (p.gb_kind == 0) && (d->path != GRAPE_B200_PATH_SMALL_CHAIN);
     if (h->seg_on) {
         SegArgs& a = h->seg;
+        a.BKL = 1;
+        while (a.BKL < K && a.BKL < 32) a.BKL <<= 1;
         int S = (int)std::ceil(std::sqrt((double)NT));
+        {
+            // GPU-filling ensembles: the two heavy kernels (formseg, seggrad: 255 registers, 8 resident warps per
+            // SM) run in whole waves of warps, each wave taking S steps, while the boundary chains take NSEG steps
+            // of about a quarter of that cost: pick the segment length that minimises waves*S + NSEG/4.
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+            const long long resident = (long long)sms * 8;
+            const long long KGR = (K + a.BKL - 1) / a.BKL, SPW = 32 / a.BKL;
+            auto cost = [&](int s_, bool& full) {
+                const long long nseg = (NT + s_ - 1) / s_;
+                const long long warps = KGR * ((nseg + SPW - 1) / SPW);
+                full = warps >= resident;
+                return (double)((warps + resident - 1) / resident) * s_ + 0.26 * (double)nseg;
+            };
+            bool full = false;
+            double best = cost(S, full);
+            if (full) {
+                const int S0 = S;
+                for (int s_ = std::max(2, S0 / 2); s_ <= std::min(64, 2 * S0); ++s_) {
+                    bool f2;
+                    const double c = cost(s_, f2);
+                    if (f2 && c < best - 1e-9) { best = c; S = s_; }
+                }
+            }
+        }
         if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
         a.S = S < 2 ? 2 : (S > 64 ? 64 : S);
         a.NSEG = (NT + a.S - 1) / a.S;
-        a.BKL = 1;
-        while (a.BKL < K && a.BKL < 32) a.BKL <<= 1;
         p.KB = (K + a.BKL - 1) / a.BKL;
         if (int rc = dev_alloc(h, &a.Pseg, (size_t)a.NSEG * NN * G)) return rc;
         if (int rc = dev_alloc(h, &a.chiE, (size_t)a.NSEG * N * K)) return rc;

@@ -56,49 +56,6 @@ GB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND
 GB_D void st_cs(cplx* p, cplx v) { __stcs(p, v); }
 GB_D cplx ld_cs(const cplx* p) { return __ldcs(p); }
 
-// Grid-wide barrier for persistent cooperative kernels (all CTAs co-resident).  cooperative_groups'
-// grid.sync() sends one atomic per CTA to ONE address: with ~120-148 CTAs the L2 serialises them
-// (~27 cycles each) and the barrier costs several microseconds, which is the whole budget of a Taylor
-// term on the latency-bound chains.  Two levels instead: CTAs arrive on one of up to 8 group counters
-// (separate 128-byte lines), the last arriver of a group bumps the top counter, everybody polls the top
-// counter.  Counters are monotonic over the kernel (zeroed by the host before the launch).
-// Ordering: data stores -> bar.sync -> fence -> relaxed RMW (group) -> [last: fence -> relaxed RMW (top)]
-// -> polled load -> fence -> bar.sync -> readers use ld.cg.
-constexpr int GBAR_GROUPS = 8;
-constexpr int GBAR_WORDS = (GBAR_GROUPS + 1) * 32;   // unsigned words to allocate and zero per kernel launch
-struct GridBarrier {
-    unsigned* grp;
-    const volatile unsigned* top_r;
-    unsigned* top;
-    unsigned gsize, ngroups, epoch;
-    GB_D void init(unsigned* base) {
-        const unsigned nb = gridDim.x;
-        ngroups = nb >= 2 * GBAR_GROUPS ? GBAR_GROUPS : 1;
-        const unsigned g = blockIdx.x % ngroups;
-        gsize = nb / ngroups + (g < nb % ngroups ? 1u : 0u);
-        grp = base + 32 * (1 + g);
-        top = base;
-        top_r = base;
-        epoch = 0;
-    }
-    GB_D void sync() {
-        ++epoch;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            const unsigned old = atomicAdd(grp, 1u);
-            if (old + 1u == epoch * gsize) {
-                __threadfence();
-                atomicAdd(top, 1u);
-            }
-            const unsigned target = epoch * ngroups;
-            while (*top_r < target) { }
-            __threadfence();
-        }
-        __syncthreads();
-    }
-};
-
 // 1/j!  j = 0..20
 __constant__ double c_invfact[21] = {
     1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,

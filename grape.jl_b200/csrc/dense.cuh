@@ -59,7 +59,6 @@ struct KryDev {
 struct DenseDev {
     int Np, Kp, Cb, RT, Pf, Pb, MS, CcapF, CcapB, nD;
     const int* kry_ok; // block-recursion backward kernels return at once if *kry_ok (nullptr: always run)
-    unsigned* bar;     // [GBAR_WORDS] grid-barrier counters of the chain kernels (zeroed before each launch)
     int mu_smem;   // backward strip kernel keeps its 8 rows of every mu_l^dagger in shared memory
     const double* Hf;
     const double* Ha;
@@ -102,12 +101,22 @@ struct DAcc {
 // DMMA mapping: A[m][k] = X[k0+k][col0+m], B[k][n] = Brow[n][k0+k], D[m][n] = out[row n][col m].
 // The operand block X was written by other CTAs one grid barrier ago and comes from L2: the loads of UK
 // k-steps are issued back to back before the first DMMA so that their latency overlaps.
-template <int NG, bool BSMEM, int UK>
+// NSET independent accumulator sets are used round-robin over the k-steps: a dependent DMMA has ~100 clk of
+// latency, and with one 8-column group per warp a single set would be a chain of kslice/4 dependent DMMAs.
+template <int NG, bool BSMEM, int UK, int NSET = 1>
 GB_D void dense_mma_slice(const double* __restrict__ Bre, const double* __restrict__ Bim, int bstride,
                           double bscale, const double* __restrict__ Xre, const double* __restrict__ Xim,
                           int ldx, const int (&col0)[NG], int ng, int kbeg, int kend, DAcc (&acc)[NG]) {
+    static_assert(UK % NSET == 0, "UK must be a multiple of NSET");
     const int lane = threadIdx.x & 31;
     const int lr = lane >> 2, lc = lane & 3;
+    DAcc loc[NSET > 1 ? NSET - 1 : 1][NG];
+    if (NSET > 1) {
+#pragma unroll
+        for (int q = 0; q < NSET - 1; ++q)
+#pragma unroll
+            for (int g = 0; g < NG; ++g) loc[q][g].zero();
+    }
     for (int kb = kbeg; kb < kend; kb += 4 * UK) {
         double are[UK][NG], aim[UK][NG];
 #pragma unroll
@@ -139,14 +148,28 @@ GB_D void dense_mma_slice(const double* __restrict__ Bre, const double* __restri
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
                     if (g < ng) {
-                        dmma884(acc[g].p1, are[u][g], bre);
-                        dmma884(acc[g].p2, aim[u][g], bim);
-                        dmma884(acc[g].q1, are[u][g], bim);
-                        dmma884(acc[g].q2, aim[u][g], bre);
+                        DAcc& a = (u % NSET == 0) ? acc[g] : loc[(u % NSET) - (NSET > 1 ? 1 : 0)][g];
+                        dmma884(a.p1, are[u][g], bre);
+                        dmma884(a.p2, aim[u][g], bim);
+                        dmma884(a.q1, are[u][g], bim);
+                        dmma884(a.q2, aim[u][g], bre);
                     }
                 }
             }
         }
+    }
+    if (NSET > 1) {
+#pragma unroll
+        for (int q = 0; q < NSET - 1; ++q)
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    acc[g].p1[e] += loc[q][g].p1[e];
+                    acc[g].p2[e] += loc[q][g].p2[e];
+                    acc[g].q1[e] += loc[q][g].q1[e];
+                    acc[g].q2[e] += loc[q][g].q2[e];
+                }
     }
 }
 
@@ -192,22 +215,48 @@ GB_D void dense_plan(const DevP& p, const DenseDev& d, int n, double dt, int& m,
     vec_plan(nrm * dt, m, s);
 }
 
-// rows r0..r0+7 of  H0 + sum_l a_l Hc_l  (or of the adjoints) into shared memory
+// rows r0..r0+7 of  H0 + sum_l a_l Hc_l  (or of the adjoints) into shared memory; the 2 x 8 loads of a trip and
+// operator are issued before their first use (this loop is pure load latency otherwise)
 GB_D void dense_form_H(const DevP& p, const double* __restrict__ Hall, int Np, int MS, int r0, int n,
                        double* __restrict__ Hs_re, double* __restrict__ Hs_im) {
     const size_t plane = (size_t)Np * Np;
-    for (int e = threadIdx.x; e < 8 * Np; e += DENSE_THREADS) {
-        const int r = e / Np, k = e % Np;
-        const size_t off = (size_t)(r0 + r) * Np + k;
-        double hr = __ldg(&Hall[off]), hi = __ldg(&Hall[plane + off]);
-        for (int l = 0; l < p.L; ++l) {
-            double a = p.eps[l * p.NT + n];
-            if (p.shape) a *= p.shape[l * p.NT + n];
-            hr = fma(a, __ldg(&Hall[(size_t)(1 + l) * 2 * plane + off]), hr);
-            hi = fma(a, __ldg(&Hall[(size_t)(1 + l) * 2 * plane + plane + off]), hi);
+    constexpr int U = 8;
+    const int tot = 8 * Np;
+    const double* __restrict__ Hrow = Hall + (size_t)r0 * Np;   // the 8 rows are contiguous: offset = e
+    for (int e0 = threadIdx.x; e0 < tot; e0 += U * DENSE_THREADS) {
+        double hr[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * DENSE_THREADS;
+            hr[u] = e < tot ? __ldg(&Hrow[e]) : 0.0;
+            hi[u] = e < tot ? __ldg(&Hrow[plane + e]) : 0.0;
         }
-        Hs_re[r * MS + k] = hr;
-        Hs_im[r * MS + k] = hi;
+        for (int l = 0; l < p.L; ++l) {
+            double al = p.eps[l * p.NT + n];
+            if (p.shape) al *= p.shape[l * p.NT + n];
+            const double* __restrict__ Hl = Hrow + (size_t)(1 + l) * 2 * plane;
+            double tr[U], ti[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * DENSE_THREADS;
+                tr[u] = e < tot ? __ldg(&Hl[e]) : 0.0;
+                ti[u] = e < tot ? __ldg(&Hl[plane + e]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                hr[u] = fma(al, tr[u], hr[u]);
+                hi[u] = fma(al, ti[u], hi[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * DENSE_THREADS;
+            if (e < tot) {
+                const int r = e / Np, k = e - r * Np;
+                Hs_re[r * MS + k] = hr[u];
+                Hs_im[r * MS + k] = hi[u];
+            }
+        }
     }
 }
 
@@ -221,11 +270,15 @@ GB_D void dense_form_H(const DevP& p, const double* __restrict__ Hall, int Np, i
 template <bool BWD>
 __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev d, KryDev kd) {
     if (BWD && !(*kd.ok)) return;   // uniform over the grid
-    GridBarrier grid;
-    grid.init(d.bar);
     extern __shared__ __align__(16) double dsm[];
     const int Np = d.Np, Kp = d.Kp, MS = d.MS, NT = p.NT;
     const int rt = blockIdx.x / d.Pf, part = blockIdx.x % d.Pf;
+    // One cooperative_groups grid barrier per Taylor term: ncu attributes ~40 % of this kernel to it (arrival skew
+    // after every CTA pulls its whole operand block from L2 at the same instant + the barrier round trips).  Two
+    // replacements were measured on C4 and were SLOWER (profiles/r1_s5_*, r1_s7_*): a two-level counter barrier
+    // with one domain per column part (+0.6 us per term) and per-producer release/acquire counters polled by every
+    // consumer warp (+1.5 us per term: thousands of pollers on two L2 lines).
+    cgx::grid_group grid = cgx::this_grid();
     const int CGtot = Kp / 8;
     const int cg0 = (part * CGtot) / d.Pf, cg1 = ((part + 1) * CGtot) / d.Pf;
     const int ncols = (cg1 - cg0) * 8, cbeg = cg0 * 8, Ccap = d.CcapF;
@@ -313,14 +366,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                 const double* src = j == 1 ? state : (kry ? slots + (size_t)(j - 1) * 2 * splane : ((j - 1) & 1 ? d.T1 : d.T0));
                 double* dst = kry ? slots + (size_t)j * 2 * splane : ((j & 1) ? d.T1 : d.T0);
                 const double x = dts / j;
-                for (int pg = cg0; pg < cg1; pg += DENSE_CGP) {
+                        for (int pg = cg0; pg < cg1; pg += DENSE_CGP) {
                     const int ng = min(DENSE_CGP, cg1 - pg);
                     cplx res;
                     if (ng == 1) {   // 8 columns per CTA (few trajectories): deeper load batches
                         int col0[1] = {pg * 8};
                         DAcc acc[1];
                         acc[0].zero();
-                        dense_mma_slice<1, true, 16>(Hs_re, Hs_im, MS, 1.0, src, src + splane, Kp, col0, 1, kbeg, kend, acc);
+                        dense_mma_slice<1, true, 8, 4>(Hs_re, Hs_im, MS, 1.0, src, src + splane, Kp, col0, 1, kbeg, kend, acc);
                         res = dense_reduce<1>(red, acc, 1);
                     } else {
                         int col0[DENSE_CGP];
@@ -796,11 +849,6 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     if ((rc = ald(&d.T1, 2 * bplane))) return rc;
     if ((rc = ald(&d.store, (size_t)(NT + 1) * 2 * splane))) return rc;
     if ((rc = ald(&d.jbpart, (size_t)dp.gridF * Kp))) return rc;
-    {
-        double* q = nullptr;
-        if ((rc = ald(&q, GBAR_WORDS / 2))) return rc;
-        d.bar = reinterpret_cast<unsigned*>(q);
-    }
     p.KB = dp.gridB;
     if ((rc = ald(&p.partial, (size_t)dp.gridB * L * NT))) return rc;
     const size_t redB = (size_t)(DENSE_THREADS / 32) * DENSE_CGP * 128;
@@ -832,7 +880,6 @@ inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int
     cudaMemcpyAsync(d.store, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     DevP pp = p;
     void* args[] = {&pp, &d, &dp.kd};
-    cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
     cudaLaunchCooperativeKernel((void*)dense_chain<false>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF, st);
     dense_tau<<<p.K, 256, 0, st>>>(p, d, dp.gridF);
     launches += 2;
@@ -848,8 +895,7 @@ inline void dense_run_backward(DensePlan& dp, const DevP& p, const cplx* chi_hos
     launches += 2;
     if (dp.kd.on) {
         void* cargs[] = {&pp, &d, &dp.kd};
-        cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
-        cudaLaunchCooperativeKernel((void*)dense_chain<true>, dim3(dp.gridF), dim3(DENSE_THREADS), cargs, dp.smemF, st);
+            cudaLaunchCooperativeKernel((void*)dense_chain<true>, dim3(dp.gridF), dim3(DENSE_THREADS), cargs, dp.smemF, st);
         launches += 1;
     }
 }

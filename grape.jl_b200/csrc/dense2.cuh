@@ -146,18 +146,134 @@ GB_D void d2_tile_gemm(double* __restrict__ sm, const double* const (&A)[LB], si
     __syncthreads();
 }
 
+// Single-operand tile GEMM of the chain kernels with 4-way split of the contraction index over the warps.
+// ncu on dense2_chain (profiles/r1_s5_ncu_c5_chain_raw.csv): DMMA pipe 51 % active, top stall "wait" --
+// with one 8x8 output tile per warp there are only two dependent accumulator chains (re, im) per warp and
+// the latency of a dependent DMMA (~100 clk) caps the rate.  Here a warp owns a 16x16 block (2x2 DMMA
+// tiles = 8 independent chains, operand fragments reused twice) over one quarter of every staged chunk;
+// the four partial sums meet in shared memory once per GEMM.  Result in the same per-thread mapping as
+// d2_tile_gemm (row wr*8+lr, columns wc*8+2lc+{0,1}).
+GB_D void d2_tile_gemm_k4(double* __restrict__ sm, const double* __restrict__ A, size_t aplane, int lda,
+                          const double* __restrict__ B, size_t bplane, int ldb, int Nk, D2Acc& out) {
+    constexpr int KC = D2_KC_F, AS = KC + 4, RS = 24;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int kq = w & 3, rh = w >> 2;
+    constexpr size_t SD = d2_stage_doubles(1, KC);
+    const double* const Aa[1] = {A};
+    const double* const Ba[1] = {B};
+    D2Acc acc[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j].re[0] = acc[i][j].re[1] = acc[i][j].im[0] = acc[i][j].im[1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < D2_ST - 1; ++s) {
+        if (s < Nk) d2_issue<1, KC>(sm + s * SD, Aa, aplane, lda, Ba, bplane, ldb, s * KC);
+        cp_async_commit();
+    }
+    for (int c = 0; c < Nk; ++c) {
+        cp_async_wait<D2_ST - 2>();
+        __syncthreads();
+        const int nx = c + D2_ST - 1;
+        if (nx < Nk) d2_issue<1, KC>(sm + (nx % D2_ST) * SD, Aa, aplane, lda, Ba, bplane, ldb, nx * KC);
+        cp_async_commit();
+        const double* st = sm + (c % D2_ST) * SD;
+        const double* bst = st + 2 * D2_TM * AS;
+#pragma unroll
+        for (int kk = 0; kk < KC / 16; ++kk) {
+            const int ko = kq * (KC / 4) + kk * 4 + lc;
+            double are[2], aim[2], bre[2], bim[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                are[i] = st[(0 * D2_TM + rh * 16 + i * 8 + lr) * AS + ko];
+                aim[i] = st[(1 * D2_TM + rh * 16 + i * 8 + lr) * AS + ko];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                bre[j] = bst[(0 * KC + ko) * D2_BS + j * 8 + lr];
+                bim[j] = bst[(1 * KC + ko) * D2_BS + j * 8 + lr];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma884(acc[i][j].re, are[i], bre[j]);
+                    dmma884(acc[i][j].im, are[i], bim[j]);
+                }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double nai = -aim[i];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    dmma884(acc[i][j].re, nai, bim[j]);
+                    dmma884(acc[i][j].im, aim[i], bre[j]);
+                }
+            }
+        }
+    }
+    __syncthreads();   // every warp is done with the stage buffers: reuse them for the partial sums
+    // red[kq][plane][row 0..31][RS]
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int row = rh * 16 + i * 8 + lr, col = j * 8 + 2 * lc;
+            *reinterpret_cast<double2*>(&sm[((kq * 2 + 0) * D2_TM + row) * RS + col]) = make_double2(acc[i][j].re[0], acc[i][j].re[1]);
+            *reinterpret_cast<double2*>(&sm[((kq * 2 + 1) * D2_TM + row) * RS + col]) = make_double2(acc[i][j].im[0], acc[i][j].im[1]);
+        }
+    __syncthreads();
+    {
+        const int wr = w >> 1, wc = w & 1;
+        const int row = wr * 8 + lr, col = wc * 8 + 2 * lc;
+        double2 r = make_double2(0.0, 0.0), im = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 a = *reinterpret_cast<const double2*>(&sm[((q * 2 + 0) * D2_TM + row) * RS + col]);
+            const double2 b = *reinterpret_cast<const double2*>(&sm[((q * 2 + 1) * D2_TM + row) * RS + col]);
+            r.x += a.x; r.y += a.y; im.x += b.x; im.y += b.y;
+        }
+        out.re[0] = r.x; out.re[1] = r.y; out.im[0] = im.x; out.im[1] = im.y;
+    }
+    __syncthreads();
+}
+
 // H_n = M_0 + sum_l a_l M_{1+l} for all matrix elements, distributed over the grid
 GB_D void d2_form(const DevP& p, const double* __restrict__ Mall, double* __restrict__ out, size_t hplane, int n) {
-    double a[DENSE_LMAX];
-    for (int l = 0; l < p.L; ++l) {
-        a[l] = p.eps[l * p.NT + n];
-        if (p.shape) a[l] *= p.shape[l * p.NT + n];
-    }
-    const size_t tot = 2 * hplane;
-    for (size_t e = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e < tot; e += (size_t)gridDim.x * D2_THREADS) {
-        double v = __ldg(&Mall[e]);
-        for (int l = 0; l < p.L; ++l) v = fma(a[l], __ldg(&Mall[(size_t)(1 + l) * tot + e]), v);
-        out[e] = v;
+    // ncu (profiles/r1_s5_ncu_c5_chain_*): written as one element per loop trip this took 18 % of the chain
+    // kernel on load latency alone; now 16-byte loads, 8 of them in flight per thread and operator.
+    constexpr int U = 8;
+    const size_t tot2 = hplane;   // double2 elements of one operator (two planes of hplane doubles)
+    const double2* __restrict__ M2 = reinterpret_cast<const double2*>(Mall);
+    double2* __restrict__ O2 = reinterpret_cast<double2*>(out);
+    const size_t stride = (size_t)gridDim.x * D2_THREADS;
+    for (size_t e0 = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e0 < tot2; e0 += U * stride) {
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t e = e0 + u * stride;
+            v[u] = e < tot2 ? __ldg(&M2[e]) : make_double2(0.0, 0.0);
+        }
+        for (int l = 0; l < p.L; ++l) {
+            double al = p.eps[l * p.NT + n];
+            if (p.shape) al *= p.shape[l * p.NT + n];
+            double2 t[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t e = e0 + u * stride;
+                t[u] = e < tot2 ? __ldg(&M2[(size_t)(1 + l) * tot2 + e]) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                v[u].x = fma(al, t[u].x, v[u].x);
+                v[u].y = fma(al, t[u].y, v[u].y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t e = e0 + u * stride;
+            if (e < tot2) O2[e] = v[u];
+        }
     }
 }
 
@@ -168,8 +284,7 @@ GB_D void d2_form(const DevP& p, const double* __restrict__ Mall, double* __rest
 template <bool BWD>
 __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d, Dense2Dev d2, KryDev kd) {
     if (BWD && !(*kd.ok)) return;   // uniform over the grid
-    GridBarrier grid;
-    grid.init(d.bar);
+    cgx::grid_group grid = cgx::this_grid();
     extern __shared__ __align__(16) double dsm[];
     __shared__ double s_gb[4][D2_TN];
     const int Np = d.Np, Kp = d.Kp, NT = p.NT;
@@ -178,7 +293,6 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
     const int lr = lane >> 2, lc = lane & 3, wr = w >> 1, wc = w & 1;
     const int NkF = Np / D2_KC_F;
     const bool gb = BWD ? (p.gb_kind != 0 && p.lambda_b != 0.0) : (p.gb_kind != 0);
-    const double one[1] = {1.0};
     double* cur = BWD ? kd.kcur : d.cur;
     double* nxt = BWD ? kd.kcur2 : d2.cur2;
     double* const cur_first = cur;
@@ -190,10 +304,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
         for (int t = blockIdx.x; t < d2.ntiles; t += gridDim.x) {
             const int rt = t / d2.tilesC, ct = t % d2.tilesC;
             const int r0 = rt * D2_TM, c0 = ct * D2_TN;
-            const double* A[1] = {d.Dm + (size_t)r0 * Np};
-            const double* B[1] = {cur + c0};
             D2Acc acc[1];
-            d2_tile_gemm<1, false, D2_KC_F>(dsm, A, hplane, Np, B, splane, Kp, NkF, one, acc);
+            d2_tile_gemm_k4(dsm, d.Dm + (size_t)r0 * Np, hplane, Np, cur + c0, splane, Kp, NkF, acc[0]);
             const int row = r0 + wr * 8 + lr;
             double v[2];
 #pragma unroll
@@ -250,8 +362,6 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
                 if (fin && has_next) d2_form(p, Hall, d2.Hn[nnext & 1], hplane, nnext);
                 for (int t = blockIdx.x; t < d2.ntiles; t += gridDim.x) {
                     const int r0 = (t / d2.tilesC) * D2_TM, c0 = (t % d2.tilesC) * D2_TN;
-                    const double* A[1] = {Hn + (size_t)r0 * Np};
-                    const double* B[1] = {src + c0};
                     const int row = r0 + wr * 8 + lr;
                     const int kc = c0 + wc * 8 + 2 * lc;
                     const size_t off = (size_t)row * Kp + kc;
@@ -260,7 +370,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
                     const double2 b_r = *reinterpret_cast<const double2*>(&base[off]);
                     const double2 b_i = *reinterpret_cast<const double2*>(&base[splane + off]);
                     D2Acc acc[1];
-                    d2_tile_gemm<1, false, D2_KC_F>(dsm, A, hplane, Np, B, splane, Kp, NkF, one, acc);
+                    d2_tile_gemm_k4(dsm, Hn + (size_t)r0 * Np, hplane, Np, src + c0, splane, Kp, NkF, acc[0]);
                     double tr[2], ti[2], vr[2], vi[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {   // forward: t = (-i x) * res ; backward: t = (+i x) * res
@@ -277,10 +387,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
                         // chi += lambda_b * 0.5 (t_{n+1} - t_{n-1}) / rho * xi(Psi(t_{n-1})), xi = -D Psi  (optimize.jl:897-908)
                         const double f = p.lambda_b * 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]);
                         const double* st = d.store + (size_t)n * 2 * splane;
-                        const double* A1[1] = {d.Dm + (size_t)r0 * Np};
-                        const double* B1[1] = {st + c0};
                         D2Acc a1[1];
-                        d2_tile_gemm<1, false, D2_KC_F>(dsm, A1, hplane, Np, B1, splane, Kp, NkF, one, a1);
+                        d2_tile_gemm_k4(dsm, d.Dm + (size_t)r0 * Np, hplane, Np, st + c0, splane, Kp, NkF, a1[0]);
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int k = kc + e;
@@ -546,7 +654,6 @@ inline void dense2_run_forward(Dense2Plan& q, DensePlan& dp, const DevP& p, cuda
     if (p.gb_kind) cudaMemsetAsync(d.jbpart, 0, (size_t)q.d2.tilesR * d.Kp * sizeof(double), st);
     DevP pp = p;
     void* args[] = {&pp, &d, &q.d2, &dp.kd};
-    cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
     cudaLaunchCooperativeKernel((void*)dense2_chain<false>, dim3(q.grid), dim3(D2_THREADS), args, q.smemF, st);
     dense_tau<<<p.K, 256, 0, st>>>(p, d, q.d2.tilesR);
     launches += 2;
@@ -570,8 +677,7 @@ inline void dense2_run_backward(Dense2Plan& q, DensePlan& dp, const DevP& p, con
     launches += 2;
     if (dp.kd.on) {
         void* cargs[] = {&pp, &d, &q.d2, &dp.kd};
-        cudaMemsetAsync(d.bar, 0, GBAR_WORDS * sizeof(unsigned), st);
-        cudaLaunchCooperativeKernel((void*)dense2_chain<true>, dim3(q.grid), dim3(D2_THREADS), cargs, q.smemF, st);
+            cudaLaunchCooperativeKernel((void*)dense2_chain<true>, dim3(q.grid), dim3(D2_THREADS), cargs, q.smemF, st);
         launches += 1;
     }
 }

@@ -60,6 +60,9 @@ struct grape_b200_handle_impl {
     WarpSegArgs wseg;
     bool seg_on;          // small path: time-segmented schedule (small_seg.cuh)
     bool interior_done;   // small path, segmented: fw_storage filled inside the segments
+    bool seg_herm;        // small path, segmented, all generators Hermitian (N <= 3): the gradient kernel recomputes
+                          // the forward states backwards; fw_storage is only filled when somebody reads it
+    bool U_valid;         // small path: p.U holds the propagators of the current pulses
     SegArgs seg;
 };
 typedef grape_b200_handle_impl H;
@@ -210,6 +213,26 @@ int small_setup(H* h, const grape_b200_problem* d) {
         if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
         a.S = S < 2 ? 2 : (S > 64 ? 64 : S);
         a.NSEG = (NT + a.S - 1) / a.S;
+        {
+            // Hermitian generators (the usual closed-system case): exp(-iH dt) is unitary and the forward state can be
+            // carried backwards next to chi. Exact test on the caller's matrices; GRAPE_B200_SEG_HERM=0 disables.
+            bool herm = N <= 3 && !(getenv("GRAPE_B200_SEG_HERM") && atoi(getenv("GRAPE_B200_SEG_HERM")) == 0);
+            auto check = [&](const double* M, size_t count) {
+                for (size_t g = 0; g < count && herm; ++g)
+                    for (int i = 0; i < N && herm; ++i)
+                        for (int j = 0; j <= i; ++j) {
+                            const double* x = M + 2 * (g * NN + (size_t)j * N + i);
+                            const double* y = M + 2 * (g * NN + (size_t)i * N + j);
+                            const double tol = 1e-15 * (std::fabs(x[0]) + std::fabs(x[1]) + std::fabs(y[0]) + std::fabs(y[1]));
+                            if (std::fabs(x[0] - y[0]) > tol || std::fabs(x[1] + y[1]) > tol) { herm = false; break; }
+                        }
+            };
+            check(d->H0, (size_t)G);
+            check(d->Hc, (size_t)G * L);
+            a.herm = herm ? 1 : 0;
+            a.store_U = herm ? 0 : 1;
+            h->seg_herm = herm;
+        }
         p.KB = (K + a.BKL - 1) / a.BKL;
         if (int rc = dev_alloc(h, &a.Pseg, (size_t)a.NSEG * NN * G)) return rc;
         if (int rc = dev_alloc(h, &a.chiE, (size_t)a.NSEG * N * K)) return rc;
@@ -289,8 +312,8 @@ void seg_chain_bwd_t(H* h, const cplx* chi_host) {
     small_segchain_bwd<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg, chi_host);
     h->launches++;
 }
-template <int N, int LCMAX>
-void seg_grad_t(H* h) {
+template <int N, int LCMAX, bool HERM>
+void seg_grad_launch(H* h) {
     const DevP& p = h->p;
     const SegArgs& a = h->seg;
     const int SPW = 32 / a.BKL;
@@ -299,11 +322,16 @@ void seg_grad_t(H* h) {
     int l0 = 0;
     while (l0 < p.L) {
         const int rem = p.L - l0;
-        if (LCMAX >= 4 && rem >= 4) { small_seggrad<N, (LCMAX >= 4 ? 4 : 1)><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 4; }
-        else if (LCMAX >= 2 && rem >= 2) { small_seggrad<N, (LCMAX >= 2 ? 2 : 1)><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 2; }
-        else { small_seggrad<N, 1><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 1; }
+        if (LCMAX >= 4 && rem >= 4) { small_seggrad<N, (LCMAX >= 4 ? 4 : 1), HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 4; }
+        else if (LCMAX >= 2 && rem >= 2) { small_seggrad<N, (LCMAX >= 2 ? 2 : 1), HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 2; }
+        else { small_seggrad<N, 1, HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 1; }
         h->launches++;
     }
+}
+template <int N, int LCMAX>
+void seg_grad_t(H* h) {
+    if (h->seg_herm) seg_grad_launch<N, LCMAX, true>(h);
+    else seg_grad_launch<N, LCMAX, false>(h);
 }
 
 #define SMALL_DISPATCH(N_, CALL1, CALL2, CALL3, CALL4) \
@@ -316,9 +344,11 @@ void run_formU(H* h) {
             if (h->seg_on && (long long)h->p.G * h->seg.NSEG >= 32768 && !getenv("GRAPE_B200_NO_FORMSEG")) {
                 // enough (generator, segment) pairs to fill the GPU: fused formation + segment product
                 SMALL_DISPATCH(h->p.N, seg_formseg_t<1>(h), seg_formseg_t<2>(h), seg_formseg_t<3>(h), seg_formseg_t<4>(h));
+                h->U_valid = h->seg.store_U != 0;
                 break;
             }
             SMALL_DISPATCH(h->p.N, small_formU_t<1>(h), small_formU_t<2>(h), small_formU_t<3>(h), small_formU_t<4>(h));
+            h->U_valid = true;
             if (h->seg_on) { SMALL_DISPATCH(h->p.N, seg_prod_t<1>(h), seg_prod_t<2>(h), seg_prod_t<3>(h), seg_prod_t<4>(h)); }
             break;
         case GRAPE_B200_PATH_WARP:
@@ -330,6 +360,10 @@ void run_formU(H* h) {
 }
 void run_fill_interior(H* h) {
     if (h->path == GRAPE_B200_PATH_SMALL && h->seg_on && !h->interior_done) {
+        if (!h->U_valid) {   // Hermitian schedule: the propagators were only accumulated into the segment products
+            SMALL_DISPATCH(h->p.N, small_formU_t<1>(h), small_formU_t<2>(h), small_formU_t<3>(h), small_formU_t<4>(h));
+            h->U_valid = true;
+        }
         SMALL_DISPATCH(h->p.N, seg_fwd_t<1>(h), seg_fwd_t<2>(h), seg_fwd_t<3>(h), seg_fwd_t<4>(h));
         h->interior_done = true;
     }
@@ -344,7 +378,7 @@ void run_forward(H* h, bool need_storage = true) {
             if (h->seg_on) {
                 SMALL_DISPATCH(h->p.N, seg_chain_fwd_t<1>(h), seg_chain_fwd_t<2>(h), seg_chain_fwd_t<3>(h), seg_chain_fwd_t<4>(h));
                 h->interior_done = false;
-                if (need_storage) run_fill_interior(h);
+                if (need_storage && !h->seg_herm) run_fill_interior(h);
                 break;
             }
             SMALL_DISPATCH(h->p.N, small_forward_t<1>(h), small_forward_t<2>(h), small_forward_t<3>(h), small_forward_t<4>(h));
@@ -369,7 +403,7 @@ void run_backward(H* h, const cplx* chi_host) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
             if (h->seg_on) {
-                run_fill_interior(h);
+                if (!h->seg_herm) run_fill_interior(h);
                 SMALL_DISPATCH(h->p.N, seg_chain_bwd_t<1>(h, chi_host), seg_chain_bwd_t<2>(h, chi_host),
                                seg_chain_bwd_t<3>(h, chi_host), seg_chain_bwd_t<4>(h, chi_host));
                 break;
@@ -500,7 +534,9 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
     if (cudaGraphLaunch(ge, h->stream) != cudaSuccess) { cudaGetLastError(); h->graphs_ok = false; return 0; }
     h->launches += gl;
     // the captured sequence of eval_f leaves the interior of fw_storage unfilled
-    if (h->seg_on || h->wseg_on) h->interior_done = grad;
+    if (h->seg_on || h->wseg_on) h->interior_done = grad && !h->seg_herm;
+    if (h->path == GRAPE_B200_PATH_SMALL)   // same bookkeeping as run_formU (not executed on a graph replay)
+        h->U_valid = !(h->seg_on && (long long)h->p.G * h->seg.NSEG >= 32768 && !getenv("GRAPE_B200_NO_FORMSEG") && !h->seg.store_U);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         h->err = "CUDA error while executing the evaluation graph";
         return -GRAPE_B200_ECUDA;
@@ -570,6 +606,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
+    h->seg_herm = false; h->U_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     h->graph_fg = nullptr; h->graph_f = nullptr; h->graph_fg_launches = h->graph_f_launches = 0;
     h->graphs_ok = !(getenv("GRAPE_B200_NO_GRAPH") && atoi(getenv("GRAPE_B200_NO_GRAPH")) != 0);
@@ -791,7 +828,10 @@ __global__ void __launch_bounds__(256) combine_grad(DevP p) {
 int grape_b200_enqueue_forward(grape_b200_handle* h, const double* d_pulsevals) {
     if (!h || !d_pulsevals) return GRAPE_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    h->p.eps = d_pulsevals;
+    // keep a handle-owned copy: lazily evaluated read-backs (fw_storage of the Hermitian schedule) need the pulses later
+    if (d_pulsevals != h->d_eps_own)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_eps_own, d_pulsevals, sizeof(double) * h->LNT, cudaMemcpyDeviceToDevice, h->stream));
+    h->p.eps = h->d_eps_own;
     rec(h, 0);
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
     run_formU(h); rec(h, 1);
@@ -833,7 +873,10 @@ int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, d
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int64_t l0 = h->launches;
     rec(h, 0);
-    h->p.eps = d_pulsevals;
+    // keep a handle-owned copy: lazily evaluated read-backs (fw_storage of the Hermitian schedule) need the pulses later
+    if (d_pulsevals != h->d_eps_own)
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_eps_own, d_pulsevals, sizeof(double) * h->LNT, cudaMemcpyDeviceToDevice, h->stream));
+    h->p.eps = h->d_eps_own;
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
     run_formU(h); rec(h, 1);
     run_forward(h); rec(h, 2); rec(h, 3);

@@ -44,8 +44,21 @@ struct BetaTable {
 };
 __constant__ BetaTable c_beta = BetaTable();
 
+// gamma(a,b) = 1/(a+b+1): coefficients of the same contraction written with the Krylov vectors of the state at the
+// END of the step (Hermitian generators, see seg_step_krylov_h)
+struct GammaTable {
+    double v[SEG_MMAX + 1][SEG_MMAX];
+    constexpr GammaTable() : v() {
+        for (int a = 0; a <= SEG_MMAX; ++a)
+            for (int b = 0; b < SEG_MMAX; ++b) v[a][b] = 1.0 / (double)(a + b + 1);
+    }
+};
+__constant__ GammaTable c_gamma = GammaTable();
+
 struct SegArgs {
     int S, NSEG;
+    int store_U;  // formseg keeps the propagators of every step in HBM (needed by the segment fill C1)
+    int herm;     // all generators Hermitian: C2 recomputes the forward states backwards, C1 is not run
     cplx* Pseg;   // [NSEG][NN][G]
     cplx* chiE;   // [NSEG][N][K]   chi_k at the END time point of each segment
     int BKL;      // lanes of a warp that enumerate trajectories (power of two <= 32)
@@ -122,9 +135,11 @@ __global__ void __launch_bounds__(128) small_formseg(DevP p, SegArgs a) {
             for (int c = 0; c < NN; ++c) P[0][c] = cscale(P[0][c], sc);
         }
         sm_expm<N, BS>(P, X, degree, s);
-        cplx* Uo = p.U + (size_t)n * NN * G + g;
+        if (a.store_U) {
+            cplx* Uo = p.U + (size_t)n * NN * G + g;
 #pragma unroll
-        for (int c = 0; c < NN; ++c) st_cs(&Uo[(size_t)c * G], X[c]);
+            for (int c = 0; c < NN; ++c) st_cs(&Uo[(size_t)c * G], X[c]);
+        }
         if (n == n0) {
 #pragma unroll
             for (int c = 0; c < NN; ++c) Pacc[c] = X[c];
@@ -369,7 +384,101 @@ GB_D void seg_step_krylov(const cplx (&A)[N * N], const cplx (&psi)[N], cplx (&c
     for (int i = 0; i < N; ++i) chi[i] = acc_chi[i];
 }
 
-template <int N, int LC>
+// Hermitian generators: the forward state is carried backwards through the segment next to chi instead of being
+// read from fw_storage (H = H^dagger, so exp(-iH dt)^{-1} = exp(+iH dt) = exp(A) with the same A = +i dt H^dagger):
+//   bt_a = A^a Psi(t_n)/a!,  ch_b = A^b chi(t_n)/b!,  Psi(t_{n-1}) = sum_a bt_a,  chi(t_{n-1}) = sum_b ch_b,
+//   M = int_0^1 Psi(s) chi(s)^dagger ds = sum_{a,b} bt_a ch_b^dagger / (a+b+1)
+// (same M as seg_step_krylov, expanded around the end of the step). On exit psi and chi hold the start-of-step states.
+template <int N>
+GB_D void seg_step_krylov_h(const cplx (&A)[N * N], cplx (&psi)[N], cplx (&chi)[N], cplx (&M)[N * N], int m) {
+    cplx e[SEG_MMAX][N];
+    cplx bv[N], acc_psi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { bv[i] = psi[i]; acc_psi[i] = psi[i]; }
+#pragma unroll
+    for (int b = 0; b < SEG_MMAX; ++b)
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[b][i] = cscale(bv[i], c_gamma.v[0][b]);
+#pragma unroll
+    for (int aa = 1; aa <= SEG_MMAX; ++aa) {
+        if (aa <= m) {
+            cplx nb[N];
+            const double inv = 1.0 / (double)aa;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], bv[q]);
+                nb[i] = cscale(acc, inv);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { bv[i] = nb[i]; acc_psi[i] = cadd(acc_psi[i], nb[i]); }
+            if (aa < m) {
+#pragma unroll
+                for (int b = 0; b < SEG_MMAX - aa; ++b)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) cfmar(e[b][i], c_gamma.v[aa][b], bv[i]);
+            }
+        }
+    }
+    cplx cv[N], acc_chi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { cv[i] = chi[i]; acc_chi[i] = chi[i]; }
+#pragma unroll
+    for (int c = 0; c < N * N; ++c) M[c] = mk(0.0, 0.0);
+#pragma unroll
+    for (int b = 0; b < SEG_MMAX; ++b) {
+        if (b < m) {
+#pragma unroll
+            for (int pp = 0; pp < N; ++pp)
+#pragma unroll
+                for (int q = 0; q < N; ++q) {   // M_pq += e_b[p] * conj(cv[q])
+                    cplx& t = M[pp * N + q];
+                    const cplx x = e[b][pp], y = cv[q];
+                    t.x = fma(x.x, y.x, t.x); t.x = fma(x.y, y.y, t.x);
+                    t.y = fma(x.y, y.x, t.y); t.y = fma(-x.x, y.y, t.y);
+                }
+            cplx nc[N];
+            const double inv = 1.0 / (double)(b + 1);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], cv[q]);
+                nc[i] = cscale(acc, inv);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { cv[i] = nc[i]; acc_chi[i] = cadd(acc_chi[i], nc[i]); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { chi[i] = acc_chi[i]; psi[i] = acc_psi[i]; }
+}
+
+// v <- exp(f A)^nsub v by the m-term Taylor recursion per sub-step
+template <int N>
+GB_D void seg_apply_exp(const cplx (&A)[N * N], cplx (&v)[N], int m, int nsub, double f) {
+    for (int sub = 0; sub < nsub; ++sub) {
+        cplx ta[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) ta[i] = v[i];
+        for (int j = 1; j <= m; ++j) {
+            const double inv = f / (double)j;
+            cplx na[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < N; ++q) cfma(acc, A[i * N + q], ta[q]);
+                na[i] = cscale(acc, inv);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { ta[i] = na[i]; v[i] = cadd(v[i], na[i]); }
+        }
+    }
+}
+
+template <int N, int LC, bool HERM>
 __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) {
     constexpr int NN = N * N;
     const int K = p.K, G = p.G, NT = p.NT;
@@ -393,9 +502,12 @@ __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) 
     cplx chi[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) chi[i] = a.chiE[((size_t)sseg * N + i) * K + kk];
+    // general generators: psin prefetches Psi(t_{n-1}) of the next step from fw_storage;
+    // Hermitian generators: psin carries the state at the END of the current step, starting from the segment
+    // boundary written by the forward chain, and is propagated backwards together with chi
     cplx psin[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) psin[i] = ld_cs(&p.psi[((size_t)(n1 - 1) * N + i) * K + kk]);
+    for (int i = 0; i < N; ++i) psin[i] = ld_cs(&p.psi[((size_t)(HERM ? n1 : n1 - 1) * N + i) * K + kk]);
 
     for (int st = 0; st < a.S; ++st) {                     // uniform trip count across the warp
         const int n = n1 - 1 - st;
@@ -404,7 +516,7 @@ __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) 
         cplx psi[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) psi[i] = psin[i];
-        if (nn - 1 >= n0) {
+        if (!HERM && nn - 1 >= n0) {
 #pragma unroll
             for (int i = 0; i < N; ++i) psin[i] = ld_cs(&p.psi[((size_t)(nn - 1) * N + i) * K + kk]);
         }
@@ -439,7 +551,13 @@ __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) 
         const bool fast = (N <= 3) && __all_sync(0xffffffffu, !taylor && s == 0 && m <= SEG_MMAX);
         if (N <= 3 && fast) {
             cplx M[NN];
-            seg_step_krylov<N>(A, psi, chi, M, m);
+            if (HERM) {
+                seg_step_krylov_h<N>(A, psi, chi, M, m);
+#pragma unroll
+                for (int i = 0; i < N; ++i) psin[i] = psi[i];
+            } else {
+                seg_step_krylov<N>(A, psi, chi, M, m);
+            }
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 double sl = sc;
@@ -456,6 +574,16 @@ __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) 
                 tg[l] = cscale(acc, rho);
             }
         } else {
+            if (HERM) {   // Psi(t_{n-1}) = exp(+i H dt) Psi(t_n), then the block recursion as for general generators
+                if (!taylor) seg_apply_exp<N>(A, psi, m, 1 << s, 1.0);
+                else {
+                    int mm, ss;
+                    vec_plan(sm_norm1<N>(A) * (dt / sc), mm, ss);
+                    seg_apply_exp<N>(A, psi, mm, 1 << ss, ldexp(1.0, -ss));
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) psin[i] = psi[i];
+            }
             // block (GradGenerator) recursion, identical to small_gradient (small_n.cuh)
             cplx E[LC][NN];
 #pragma unroll

@@ -191,3 +191,84 @@ def test_warp_functional_only_and_host_chi(lib_built):
     Gp = np.zeros_like(eps)
     eh.backward_chi(chi, Gp)
     assert np.max(np.abs(Gp - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+
+
+# ---- Hermitian schedule: forward states recomputed backwards inside the gradient kernel (csrc/small_seg.cuh,
+# ---- seg_step_krylov_h), fw_storage filled lazily; GRAPE_B200_SEG_HERM=0 selects the general schedule
+@pytest.fixture
+def herm_mode(request):
+    old = os.environ.get("GRAPE_B200_SEG_HERM")
+    os.environ["GRAPE_B200_SEG_HERM"] = str(request.param)
+    yield request.param
+    if old is None:
+        del os.environ["GRAPE_B200_SEG_HERM"]
+    else:
+        os.environ["GRAPE_B200_SEG_HERM"] = old
+
+
+@pytest.mark.parametrize("herm_mode", [1, 0], indirect=True)
+@pytest.mark.parametrize("seg_len", [2, 7, 64], indirect=True)
+@pytest.mark.parametrize("N", [1, 2, 3])
+def test_hermitian_schedule_small_theta(lib_built, herm_mode, seg_len, N):
+    p, eps = configs.random_problem(K=5, N=N, L=2, NT=37, seed=300 + N, hermitian=True, shaped=True, functional=gb.SM)
+    p.tlist[:] = p.tlist * 0.02
+    check(p, eps)
+
+
+@pytest.mark.parametrize("herm_mode", [1, 0], indirect=True)
+@pytest.mark.parametrize("K", [1, 3, 33, 70])
+def test_hermitian_schedule_lane_mapping_and_large_theta(lib_built, herm_mode, K):
+    """large ||H dt|| (sub-steps, block recursion in the gradient kernel) with Hermitian generators"""
+    p, eps = configs.random_problem(K=K, N=3, L=3, NT=19, seed=310 + K, hermitian=True, uniform=True, functional=gb.SS)
+    check(p, eps)
+    p, eps = configs.random_problem(K=K, N=2, L=1, NT=23, seed=320 + K, hermitian=True, functional=gb.RE)
+    p.tlist[:] = p.tlist * 0.05
+    check(p, eps)
+
+
+@pytest.mark.parametrize("herm_mode", [1, 0], indirect=True)
+def test_hermitian_schedule_taylor_method(lib_built, herm_mode):
+    p, eps = configs.random_problem(K=4, N=3, L=2, NT=21, seed=331, hermitian=True, gradient_method=gb.TAYLOR)
+    p.tlist[:] = p.tlist * 0.1
+    check(p, eps)
+
+
+def test_hermitian_schedule_lazy_storage_follows_the_pulses(lib_built):
+    """fw_storage is filled on demand from the pulses of the LAST evaluation (also after a graph replay and after
+    the device-pointer entry points)"""
+    import torch
+    p, eps = configs.c3_ensemble(n_delta=6, n_amp=5, NT=90)
+    op = go.from_problem(p)
+    e = engine(p)
+    G = np.zeros_like(eps)
+    for scale in (1.0, 0.6, 1.3):
+        x = eps * scale
+        ref = go.evaluate_gradient(op, x)
+        J = e.evaluate_gradient(G, x)
+        assert abs(J - ref["J"]) <= RTOL and np.max(np.abs(G - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+        assert np.max(np.abs(e.stored_states(7) - ref["storage"][7])) <= 1e-12
+        assert np.max(np.abs(e.final_states() - ref["final_states"])) <= 1e-12
+    x = eps * 0.8
+    ref = go.evaluate_gradient(op, x)
+    d_x = torch.from_numpy(x).cuda()
+    d_G = torch.zeros_like(d_x)
+    e.eval_fg_device(d_x.data_ptr(), d_G.data_ptr(), None)
+    assert np.max(np.abs(d_G.cpu().numpy() - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+    assert np.max(np.abs(e.stored_states(11) - ref["storage"][11])) <= 1e-12
+    assert np.max(np.abs(e.tau_grads(11) - ref["tau_grads"][11])) <= 1e-12
+    e.close()
+
+
+def test_c3_full_size_hermitian_vs_general_schedule(lib_built):
+    """BASELINE configs[2] at full size: the two schedules agree to 1e-12 on every gradient element"""
+    p, eps = configs.c3_ensemble()
+    e, J, G = run(p, eps)
+    e.close()
+    os.environ["GRAPE_B200_SEG_HERM"] = "0"
+    try:
+        e0, J0, G0 = run(p, eps)
+        e0.close()
+    finally:
+        del os.environ["GRAPE_B200_SEG_HERM"]
+    assert abs(J - J0) < 1e-13
+    assert np.max(np.abs(G - G0)) <= 1e-12 * np.max(np.abs(G0))

@@ -111,15 +111,19 @@ def cpu_reference_run(p, eps, sample_k, sample_nt, steps, warmup):
     """Times the C restatement of the reference algorithm (oracle/grape_oracle_c.c)
     on all host threads over a bounded sample of the workload."""
     from oracle import c_oracle as co
-    cores = co.max_threads()
+    # all host cores this process may use; torchrun exports OMP_NUM_THREADS=1, so the count is passed explicitly
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or co.max_threads()
     sample_k = min(sample_k, p.K)
     sample_nt = min(sample_nt, p.NT)
     for _ in range(warmup):
-        co.evaluate_gradient(p, eps, k_count=min(sample_k, 4 * cores), nt_count=min(sample_nt, 50))
+        co.evaluate_gradient(p, eps, k_count=min(sample_k, 4 * cores), nt_count=min(sample_nt, 50), nthreads=cores)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        co.evaluate_gradient(p, eps, k_count=sample_k, nt_count=sample_nt)
+        co.evaluate_gradient(p, eps, k_count=sample_k, nt_count=sample_nt, nthreads=cores)
         ts.append(time.perf_counter() - t0)
     t = float(np.mean(ts))
     return dict(value=sample_k * sample_nt / t, unit=UNIT, cores=cores, kind="port",

@@ -50,11 +50,13 @@ def make_workload(name, world=1, scaling="weak"):
         p, eps = configs.c2_transmon()
         desc = dict(workload="c2_transmon_xgate K=4 N=6 L=2 NT=2000 J_T_sm (BASELINE configs[1])")
     elif name == "c4":
-        p, eps = configs.c4_dense450()
-        desc = dict(workload="c4_dense N=450 K=16 L=2 NT=5000 J_T_sm (BASELINE configs[3])")
+        kw = 16 * (world if scaling == "weak" else 1)      # weak scaling: 16 basis trajectories per GPU
+        p, eps = configs.c4_dense450(K=kw)
+        desc = dict(workload=f"c4_dense N=450 K={kw} L=2 NT=5000 J_T_sm (BASELINE configs[3])")
     elif name == "c5":
-        p, eps = configs.c5_dense1024()
-        desc = dict(workload="c5_dense N=1024 K=64 L=2 NT=1000 J_T_sm+J_a+g_b (BASELINE configs[4])")
+        kw = 64 * (world if scaling == "weak" else 1)      # weak scaling: 64 trajectories per GPU
+        p, eps = configs.c5_dense1024(K=kw)
+        desc = dict(workload=f"c5_dense N=1024 K={kw} L=2 NT=1000 J_T_sm+J_a+g_b (BASELINE configs[4])")
     else:
         raise SystemExit(f"unknown workload {name}")
     desc.update(K=p.K, N=p.N, L=p.L, NT=p.NT, units_per_step=p.K * p.NT)

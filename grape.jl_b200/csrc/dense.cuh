@@ -772,7 +772,20 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int Np = (N + 31) / 32 * 32, Kp = (K + 7) / 8 * 8, Cb = (L + 1) * Kp;
+    const int Np = (N + 31) / 32 * 32;
+    int Kp = (K + 7) / 8 * 8;
+    {
+        // can the 8-row strip kernels serve this problem (one row strip per SM, tile in shared memory)?  If not, the
+        // tiled kernels (dense2.cuh) must: they need the trajectory block padded to their 16-column tile.
+        const int RT = Np / 8, MS = Np + 4, Cb8 = (L + 1) * Kp;
+        const int Pf = std::max(1, std::min(std::max(1, sms / RT), Kp / 8)), Pb = std::max(1, std::min(std::max(1, sms / RT), Cb8 / 8));
+        const size_t CcF = ((Kp / 8 + Pf - 1) / Pf) * 8, CcB = ((Cb8 / 8 + Pb - 1) / Pb) * 8;
+        const size_t redB = (size_t)(DENSE_THREADS / 32) * DENSE_CGP * 128;
+        const size_t sF = sizeof(double) * (16 * (size_t)MS + 16 * CcF + redB + CcF + 8);
+        const size_t sB = sizeof(double) * (16 * (size_t)MS + 16 * CcB + redB + 64);
+        if (RT > sms || sF > 227 * 1024 || sB > 227 * 1024) Kp = (K + 15) / 16 * 16;
+    }
+    const int Cb = (L + 1) * Kp;
     d.Np = Np; d.Kp = Kp; d.Cb = Cb; d.RT = Np / 8; d.MS = Np + 4; d.nD = p.gb_nD;
     if (d.RT > sms) { dp.strip_ok = false; dp.strip_err = "dense strip kernels need ceil32(N)/8 <= number of SMs (N <= 1184 on B200)"; }
     d.Pf = std::max(1, std::min(std::max(1, sms / d.RT), Kp / 8));

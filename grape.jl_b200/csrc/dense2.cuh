@@ -597,7 +597,8 @@ inline int dense2_setup(Dense2Plan& q, DensePlan& dp, DevP& p, std::vector<void*
     d2.ntiles = d2.tilesR * d2.tilesC;
     const bool force = getenv("GRAPE_B200_DENSE2") && atoi(getenv("GRAPE_B200_DENSE2")) == 1;
     const bool off = getenv("GRAPE_B200_DENSE2") && atoi(getenv("GRAPE_B200_DENSE2")) == 0;
-    if (off || (!force && d2.ntiles < 64)) return 0;    // few tiles: the strip kernels (dense.cuh) use more SMs
+    // few tiles: the strip kernels (dense.cuh) use more SMs -- if they can run at all
+    if ((off || (!force && d2.ntiles < 64)) && dp.strip_ok) return 0;
     q.smemF = sizeof(double) * d2_stage_doubles(1, D2_KC_F) * D2_ST;
     q.smemB = std::max(sizeof(double) * d2_stage_doubles(LB, D2_KC_B) * D2_ST, q.smemF);
     if (q.smemB > 200 * 1024) return 0;

@@ -186,3 +186,22 @@ def test_c5_full_width_forms_agree(lib_built):
         e.close()
     assert abs(res[0][0] - res[1][0]) <= 1e-12
     assert np.max(np.abs(res[0][1] - res[1][1])) <= 1e-11 * np.max(np.abs(res[1][1]))
+
+
+def test_large_n_few_trajectories_uses_tiled_kernels(lib_built):
+    """N = 1216 > 1184: more 8-row strips than SMs, so the strip kernels cannot run; the trajectory block is padded
+    to the 16-column tile and the tiled kernels serve both backward forms.  Oracle: the :taylor variant (N x N
+    exponentials only), which agrees with :gradgen to 1e-14 (tests/test_oracle_known_answers.py)."""
+    p, eps = configs.c4_dense450(N=1216, K=3, NT=2)
+    ref = go.evaluate_gradient(go.from_problem(p, gradient_method=go.TAYLOR), eps)
+    scale = np.max(np.abs(ref["G"]))
+    for kry in (1, 0):
+        with _Env(GRAPE_B200_KRYLOV=kry):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        J = e.evaluate_gradient(G, eps)
+        assert e.gradient_form() == kry
+        assert abs(J - ref["J"]) <= 1e-10
+        assert np.max(np.abs(G - ref["G"])) <= 1e-10 * scale
+        assert np.max(np.abs(e.final_states() - ref["final_states"])) <= 1e-12
+        e.close()

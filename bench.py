@@ -378,13 +378,16 @@ def main():
                                     peak_source=peak_src, kernel_ms=k_ms, algorithmic_bytes_per_unit=b_unit,
                                     phase_ms=dict(zip(names, [float(v) for v in phase[:5]])),
                                     share_of_step=k_ms / float(phase[6]) if phase[6] > 0 else None)
-            fl_unit = pk.executed_flops_per_unit(p, eps)
+            sched = eng.small_schedule()
+            fl_unit = pk.executed_flops_per_unit(p, eps, schedule=sched)
             line["roofline_fp64"] = dict(
                 bound="fp64_fma", note="the small-N kernels are FP64-FMA bound, not HBM bound (SURVEY 8d); "
                                        "flops are the FP64 work the kernels execute (model in grape.jl_b200/peaks.py), step-level",
                 achieved=fl_unit * units_per_step / (ms_per_step * 1e-3) / 1e12, unit="TFLOP/s",
                 peak=fp["dfma_tflops"], peak_source="measured on this GPU in this run (csrc/peaks.cu DFMA loop)",
                 dmma_peak=fp["dmma_tflops"], flops_per_unit=fl_unit,
+                small_schedule={0: "n/a", 1: "segmented, general generators", 2: "segmented, Hermitian generators",
+                                3: "segmented, real-symmetric generators"}.get(sched, str(sched)),
                 frac=fl_unit * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dfma_tflops"] if fp["dfma_tflops"] > 0 else None)
         if not args.no_cpu_baseline:
             sk, snt = cpu_sample_size(args.workload)

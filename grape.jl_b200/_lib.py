@@ -62,6 +62,7 @@ SYMBOLS = {
     "grape_b200_stream": (_P, [_P]),
     "grape_b200_launch_count": (C.c_int64, [_P]),
     "grape_b200_gradient_form": (C.c_int, [_P]),
+    "grape_b200_small_schedule": (C.c_int, [_P]),
 }
 
 _lib = None

@@ -162,15 +162,18 @@ def c5_dense1024(N=1024, K=64, NT=1000, **kw):
 
 
 def random_problem(K=3, N=3, L=2, NT=12, G=None, seed=0, hermitian=True, uniform=False,
-                   shaped=False, **kw):
+                   shaped=False, real=False, **kw):
     """Randomised small problem (non-uniform grid, optionally non-Hermitian
-    generators, cf. reference test/test_taylor_grad.jl:17-20)."""
+    generators, cf. reference test/test_taylor_grad.jl:17-20; `real`: real-symmetric
+    generators, the rotating-frame / real-control case)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     G = K if G is None else G
 
     def rmat():
         A = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
-        return (A + A.conj().T) / 2 if hermitian else A
+        if real:
+            A = A.real + 0j
+        return (A + A.conj().T) / 2 if (hermitian or real) else A
 
     H0 = np.stack([rmat() for _ in range(G)])
     Hc = np.stack([np.stack([rmat() for _ in range(L)]) for _ in range(G)])

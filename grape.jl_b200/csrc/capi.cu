@@ -10,6 +10,7 @@
 #include "reduce.cuh"
 #include "small_n.cuh"
 #include "small_seg.cuh"
+#include "small_sym.cuh"
 #include "warp_n.cuh"
 #include "warp_seg.cuh"
 #include "dense.cuh"
@@ -63,6 +64,11 @@ struct grape_b200_handle_impl {
     bool seg_herm;        // small path, segmented, all generators Hermitian (N <= 3): the gradient kernel recomputes
                           // the forward states backwards; fw_storage is only filled when somebody reads it
     bool U_valid;         // small path: p.U holds the propagators of the current pulses
+    bool seg_fuse;        // small path, segmented: fused propagator formation + segment product (small_formseg)
+    int sym_occ;          // resident CTAs per SM small_seggrad_sym is compiled for (3; GRAPE_B200_SYM_OCC=2: no spills, 8 warps)
+    bool seg_real;        // seg_herm and every generator real (symmetric): real-arithmetic kernels of small_sym.cuh
+    cplx* d_taugrads;     // [K][L][NT] dump buffer of get_tau_grads (allocated on first use)
+    bool taugrads_valid;  // d_taugrads holds the tau_grads of the last backward sweep
     SegArgs seg;
 };
 typedef grape_b200_handle_impl H;
@@ -232,7 +238,39 @@ int small_setup(H* h, const grape_b200_problem* d) {
             a.herm = herm ? 1 : 0;
             a.store_U = herm ? 0 : 1;
             h->seg_herm = herm;
+            // real symmetric generators: real-arithmetic segment products and gradient contraction (small_sym.cuh).
+            // Exact test (every imaginary part is zero); GRAPE_B200_SEG_REAL=0 disables.
+            bool real = herm && !(getenv("GRAPE_B200_SEG_REAL") && atoi(getenv("GRAPE_B200_SEG_REAL")) == 0);
+            for (size_t e = 0; e < (size_t)G * NN && real; ++e) real = d->H0[2 * e + 1] == 0.0;
+            for (size_t e = 0; e < (size_t)G * L * NN && real; ++e) real = d->Hc[2 * e + 1] == 0.0;
+            h->seg_real = real;
+            h->sym_occ = getenv("GRAPE_B200_SYM_OCC") ? atoi(getenv("GRAPE_B200_SYM_OCC")) : 3;
+            if (real) {
+                std::vector<double> rb((size_t)NN * G);
+                for (int g = 0; g < G; ++g)
+                    for (int i = 0; i < N; ++i)
+                        for (int j = 0; j < N; ++j)
+                            rb[(size_t)(i * N + j) * G + g] = d->H0[2 * ((size_t)g * NN + (size_t)j * N + i)];
+                double* rq;
+                if (int rc = dev_upload(h, &rq, rb.data(), rb.size())) return rc;
+                a.H0r = rq;
+                rb.assign((size_t)L * NN * G, 0.0);
+                for (int g = 0; g < G; ++g)
+                    for (int l = 0; l < L; ++l)
+                        for (int i = 0; i < N; ++i)
+                            for (int j = 0; j < N; ++j)
+                                rb[((size_t)l * NN + i * N + j) * G + g] = d->Hc[2 * (((size_t)g * L + l) * NN + (size_t)j * N + i)];
+                if (int rc = dev_upload(h, &rq, rb.data(), rb.size())) return rc;
+                a.Hcr = rq;
+                if (int rc = dev_alloc(h, &a.notfast, 1)) return rc;
+                CUDA_TRY(h, cudaMemset(a.notfast, 0, sizeof(int)));
+            }
         }
+        // enough (generator, segment) pairs to fill the GPU: one thread forms the propagators of its segment and their
+        // product; GRAPE_B200_NO_FORMSEG=1 / GRAPE_B200_FORCE_FORMSEG=1 override the size rule (tests)
+        h->seg_fuse = (long long)G * a.NSEG >= 32768;
+        if (getenv("GRAPE_B200_FORCE_FORMSEG") && atoi(getenv("GRAPE_B200_FORCE_FORMSEG")) != 0) h->seg_fuse = true;
+        if (getenv("GRAPE_B200_NO_FORMSEG")) h->seg_fuse = false;
         p.KB = (K + a.BKL - 1) / a.BKL;
         if (int rc = dev_alloc(h, &a.Pseg, (size_t)a.NSEG * NN * G)) return rc;
         if (int rc = dev_alloc(h, &a.chiE, (size_t)a.NSEG * N * K)) return rc;
@@ -293,7 +331,12 @@ void seg_prod_t(H* h) {
 template <int N>
 void seg_formseg_t(H* h) {
     const long long tot = (long long)h->p.G * h->seg.NSEG;
-    small_formseg<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+    if (N <= 3 && h->seg_real) {
+        cudaMemsetAsync(h->seg.notfast, 0, sizeof(int), h->stream);
+        small_formseg_sym<(N <= 3 ? N : 1)><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+    } else {
+        small_formseg<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+    }
     h->launches++;
 }
 template <int N>
@@ -312,8 +355,14 @@ void seg_chain_bwd_t(H* h, const cplx* chi_host) {
     small_segchain_bwd<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg, chi_host);
     h->launches++;
 }
+// the fused formation + segment-product kernel runs (enough (generator, segment) pairs to fill the GPU)
+bool seg_fused(const H* h) { return h->seg_on && h->seg_fuse; }
+// the real-symmetric gradient kernel may serve this call: its eligibility flag was written by small_formseg_sym
+bool seg_real_active(const H* h) {
+    return h->seg_real && seg_fused(h) && h->p.grad_method == 0 && !h->p.taugrads;
+}
 template <int N, int LCMAX, bool HERM>
-void seg_grad_launch(H* h) {
+void seg_grad_launch(H* h, const int* run_if) {
     const DevP& p = h->p;
     const SegArgs& a = h->seg;
     const int SPW = 32 / a.BKL;
@@ -322,16 +371,28 @@ void seg_grad_launch(H* h) {
     int l0 = 0;
     while (l0 < p.L) {
         const int rem = p.L - l0;
-        if (LCMAX >= 4 && rem >= 4) { small_seggrad<N, (LCMAX >= 4 ? 4 : 1), HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 4; }
-        else if (LCMAX >= 2 && rem >= 2) { small_seggrad<N, (LCMAX >= 2 ? 2 : 1), HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 2; }
-        else { small_seggrad<N, 1, HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0); l0 += 1; }
+        if (LCMAX >= 4 && rem >= 4) { small_seggrad<N, (LCMAX >= 4 ? 4 : 1), HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0, run_if); l0 += 4; }
+        else if (LCMAX >= 2 && rem >= 2) { small_seggrad<N, (LCMAX >= 2 ? 2 : 1), HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0, run_if); l0 += 2; }
+        else { small_seggrad<N, 1, HERM><<<blocks, 128, 0, h->stream>>>(p, a, l0, run_if); l0 += 1; }
         h->launches++;
     }
 }
 template <int N, int LCMAX>
 void seg_grad_t(H* h) {
-    if (h->seg_herm) seg_grad_launch<N, LCMAX, true>(h);
-    else seg_grad_launch<N, LCMAX, false>(h);
+    const int* run_if = nullptr;
+    if (N <= 3 && seg_real_active(h)) {
+        // real-symmetric generators: all controls in one launch; if a step of this call is not eligible (flag written by
+        // small_formseg_sym) the kernel returns at once and the general Hermitian kernel below runs instead
+        const SegArgs& a = h->seg;
+        const int SPW = 32 / a.BKL;
+        const long long warps = (long long)((h->p.K + a.BKL - 1) / a.BKL) * ((a.NSEG + SPW - 1) / SPW);
+        if (h->sym_occ == 2) small_seggrad_sym<(N <= 3 ? N : 1), 2><<<(unsigned)((warps + 3) / 4), 128, 0, h->stream>>>(h->p, a);
+        else small_seggrad_sym<(N <= 3 ? N : 1), 3><<<(unsigned)((warps + 3) / 4), 128, 0, h->stream>>>(h->p, a);
+        h->launches++;
+        run_if = a.notfast;
+    }
+    if (h->seg_herm) seg_grad_launch<N, LCMAX, true>(h, run_if);
+    else seg_grad_launch<N, LCMAX, false>(h, run_if);
 }
 
 #define SMALL_DISPATCH(N_, CALL1, CALL2, CALL3, CALL4) \
@@ -341,7 +402,7 @@ void seg_grad_t(H* h) {
 void run_formU(H* h) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
-            if (h->seg_on && (long long)h->p.G * h->seg.NSEG >= 32768 && !getenv("GRAPE_B200_NO_FORMSEG")) {
+            if (seg_fused(h)) {
                 // enough (generator, segment) pairs to fill the GPU: fused formation + segment product
                 SMALL_DISPATCH(h->p.N, seg_formseg_t<1>(h), seg_formseg_t<2>(h), seg_formseg_t<3>(h), seg_formseg_t<4>(h));
                 h->U_valid = h->seg.store_U != 0;
@@ -536,7 +597,7 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
     // the captured sequence of eval_f leaves the interior of fw_storage unfilled
     if (h->seg_on || h->wseg_on) h->interior_done = grad && !h->seg_herm;
     if (h->path == GRAPE_B200_PATH_SMALL)   // same bookkeeping as run_formU (not executed on a graph replay)
-        h->U_valid = !(h->seg_on && (long long)h->p.G * h->seg.NSEG >= 32768 && !getenv("GRAPE_B200_NO_FORMSEG") && !h->seg.store_U);
+        h->U_valid = !(seg_fused(h) && !h->seg.store_U);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
         h->err = "CUDA error while executing the evaluation graph";
         return -GRAPE_B200_ECUDA;
@@ -604,9 +665,9 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     h->d_out = nullptr; h->h_out = nullptr; h->h_in = nullptr; h->d_chi_host = nullptr;
     h->d_tmp = nullptr; h->tmp_elems = 0; h->stream = nullptr;
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
-    h->profiling = false; h->forward_done = false; h->backward_done = false; h->launches = 0;
+    h->profiling = false; h->forward_done = false; h->backward_done = false; h->taugrads_valid = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
-    h->seg_herm = false; h->U_valid = false;
+    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->d_taugrads = nullptr; h->taugrads_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     h->graph_fg = nullptr; h->graph_f = nullptr; h->graph_fg_launches = h->graph_f_launches = 0;
     h->graphs_ok = !(getenv("GRAPE_B200_NO_GRAPH") && atoi(getenv("GRAPE_B200_NO_GRAPH")) != 0);
@@ -724,7 +785,7 @@ int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals, double* J_p
         if (int rc = download_all(h)) return rc;
         collect_timings(h, l0);
     }
-    h->forward_done = true; h->backward_done = false;
+    h->forward_done = true; h->backward_done = false; h->taugrads_valid = false;
     if (h->p.functional == GRAPE_B200_JT_HOST) h->h_out[h->off_J] = 0.0 / 0.0;
     copy_out_common(h, J_parts, tau);
     return check_flags(h);
@@ -753,7 +814,7 @@ int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G,
         if (int rc = download_all(h)) return rc;
         collect_timings(h, l0);
     }
-    h->forward_done = true; h->backward_done = true;
+    h->forward_done = true; h->backward_done = true; h->taugrads_valid = false;
     const int LNT = h->LNT;
     memcpy(G, h->h_out, sizeof(double) * LNT);
     if (grad_J_Tb) memcpy(grad_J_Tb, h->h_out + LNT, sizeof(double) * LNT);
@@ -773,7 +834,7 @@ int grape_b200_forward(grape_b200_handle* h, const double* pulsevals, double* ta
     // only sums + tau + flags are needed, but one copy of the block is cheapest
     if (int rc = download_all(h)) return rc;
     collect_timings(h, l0);
-    h->forward_done = true; h->backward_done = false;
+    h->forward_done = true; h->backward_done = false; h->taugrads_valid = false;
     if (tau) memcpy(tau, h->h_out + h->off_tau, 2 * sizeof(double) * h->p.K);
     if (sums) memcpy(sums, h->h_out + h->off_sums, 4 * sizeof(double));
     return check_flags(h);
@@ -788,7 +849,7 @@ static int backward_common(grape_b200_handle* h, const cplx* chi_host, double* G
     run_finalize(h, true); rec(h, 5);
     if (int rc = download_all(h)) return rc;
     collect_timings(h, l0);
-    h->backward_done = true;
+    h->backward_done = true; h->taugrads_valid = false;
     const int LNT = h->LNT;
     if (G_partial) memcpy(G_partial, h->h_out + LNT, sizeof(double) * LNT);   // grad_J_Tb partial
     if (grad_J_a) memcpy(grad_J_a, h->h_out + 2 * LNT, sizeof(double) * LNT);
@@ -836,7 +897,7 @@ int grape_b200_enqueue_forward(grape_b200_handle* h, const double* d_pulsevals) 
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
     run_formU(h); rec(h, 1);
     run_forward(h); rec(h, 2); rec(h, 3);
-    h->forward_done = true; h->backward_done = false;
+    h->forward_done = true; h->backward_done = false; h->taugrads_valid = false;
     return 0;
 }
 int grape_b200_enqueue_backward(grape_b200_handle* h) {
@@ -847,7 +908,7 @@ int grape_b200_enqueue_backward(grape_b200_handle* h) {
     run_backward(h, nullptr); rec(h, 4);
     run_gradient(h);
     run_finalize(h, true); rec(h, 5); rec(h, 6);
-    h->backward_done = true;
+    h->backward_done = true; h->taugrads_valid = false;
     return 0;
 }
 int grape_b200_enqueue_combine(grape_b200_handle* h) {
@@ -891,7 +952,7 @@ int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, d
     CUDA_TRY(h, cudaGetLastError());
     collect_timings(h, l0);
     h->p.eps = h->d_eps_own;
-    h->forward_done = true; h->backward_done = true;
+    h->forward_done = true; h->backward_done = true; h->taugrads_valid = false;
     return check_flags(h);
 }
 
@@ -974,18 +1035,21 @@ int grape_b200_get_tau_grads(grape_b200_handle* h, int32_t k, double* out) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     DevP& p = h->p;
     const size_t per = (size_t)p.L * p.NT;
-    if (!p.taugrads) {
-        cplx* q;
-        if (int rc = dev_alloc(h, &q, per * p.K)) return rc;
-        p.taugrads = q;
-        // re-run the contraction with the dump enabled (states are still resident)
-        if (h->path == GRAPE_B200_PATH_DENSE) {
-            h->err = "tau_grads dump is not available on the dense path";
-            return GRAPE_B200_EINVAL;
-        }
-        run_gradient(h);
+    if (h->path == GRAPE_B200_PATH_DENSE) {
+        h->err = "tau_grads dump is not available on the dense path";
+        return GRAPE_B200_EINVAL;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(out, p.taugrads + (size_t)k * per, per * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->taugrads_valid) {
+        if (!h->d_taugrads)
+            if (int rc = dev_alloc(h, &h->d_taugrads, per * p.K)) return rc;
+        // re-run the contraction of the last backward sweep with the dump enabled (states are still resident);
+        // the dump pointer is only set for this launch, so evaluation calls never pay for it
+        p.taugrads = h->d_taugrads;
+        run_gradient(h);
+        p.taugrads = nullptr;
+        h->taugrads_valid = true;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_taugrads + (size_t)k * per, per * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1024,6 +1088,20 @@ int grape_b200_gradient_form(grape_b200_handle* h) {
         return -GRAPE_B200_ECUDA;
     }
     return ok ? 1 : 0;
+}
+
+int grape_b200_small_schedule(grape_b200_handle* h) {
+    if (!h) return -GRAPE_B200_EINVAL;
+    if (h->path != GRAPE_B200_PATH_SMALL || !h->seg_on) return 0;
+    if (!h->seg_herm) return 1;
+    if (!seg_real_active(h)) return 2;
+    int nf = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
+        cudaMemcpy(&nf, h->seg.notfast, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        h->err = "CUDA error while reading the schedule flag";
+        return -GRAPE_B200_ECUDA;
+    }
+    return nf ? 2 : 3;
 }
 
 }  // extern "C"

@@ -62,6 +62,10 @@ struct SegArgs {
     cplx* Pseg;   // [NSEG][NN][G]
     cplx* chiE;   // [NSEG][N][K]   chi_k at the END time point of each segment
     int BKL;      // lanes of a warp that enumerate trajectories (power of two <= 32)
+    // real-symmetric generators (small_sym.cuh): real copies of the operators and the device-side eligibility flag
+    const double* H0r;   // [NN][G]
+    const double* Hcr;   // [L][NN][G]
+    int* notfast;        // [1] set by small_formseg_sym when a step needs > SEG_MMAX orders or sub-stepping
 };
 
 // ---------------------------------------------------------------------------
@@ -479,8 +483,9 @@ GB_D void seg_apply_exp(const cplx (&A)[N * N], cplx (&v)[N], int m, int nsub, d
 }
 
 template <int N, int LC, bool HERM>
-__global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0) {
+__global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0, const int* __restrict__ run_if) {
     constexpr int NN = N * N;
+    if (run_if && !*run_if) return;   // uniform over the grid: small_seggrad_sym served this call
     const int K = p.K, G = p.G, NT = p.NT;
     const int lane = threadIdx.x & 31;
     const int BKL = a.BKL, SPW = 32 / BKL;                 // segments per warp

@@ -1,0 +1,314 @@
+// small_sym.cuh -- real-symmetric generators on the time-segmented schedule of the N <= 3 path.
+//
+// Closed-system control problems in a rotating frame with real control fields have
+// H0 and every control operator real and symmetric (README two-level system, the
+// Lambda system of test/test_state_running_cost.jl:183-227).  Then A = +i dt H^dagger
+// = i Hs with Hs = dt H REAL, and both steps of the schedule of small_seg.cuh are done
+// in real matrix arithmetic on complex vectors:
+//
+//   A2' small_formseg_sym   U_n = exp(-i Hs) = cos(Hs) - i sin(Hs); cos and sin are
+//        polynomials in the real matrix Q = Hs^2 (the even / odd halves of the same
+//        degree-3/7/11/15 Taylor polynomial exp_plan() prescribes), a real N x N product
+//        costs a quarter of a complex one; P_seg <- U_n P_seg is four real products.
+//   C2' small_seggrad_sym   Krylov vectors of the END-of-step states (seg_step_krylov_h)
+//        written with the un-normalised real-matrix powers  w_a = Hs^a Psi, x_b = Hs^b chi:
+//          bt_a = i^a w_a / a!,   ch_b = i^b x_b / b!      (i^a = swap / negate, free)
+//          Psi(t_{n-1}) = sum_a bt_a,  chi(t_{n-1}) = sum_b ch_b
+//          M = sum_{a+b<=m-1} bt_a ch_b^dagger/(a+b+1) = sum_b e_b (i^b x_b)^dagger,
+//          e_b = sum_a kappa(a,b) i^a w_a,  kappa(a,b) = 1/((a+b+1) a! b!)
+//        and because E_l = i s_l mu_l^dagger has a REAL mu_l, the gradient element
+//          Re tau_grad[k][n,l] = rho_k s_l sum_pq mu_l[p,q] Im M[p,q]     (optimize.jl:893-895, 574-584)
+//        needs only Im M.  The Taylor order is the warp maximum, so the step is a
+//        branch-free, fully unrolled template <M>.
+//
+// Same truncation as the m-term GradGenerator block recursion (a + b <= m - 1), hence the
+// same numbers as small_seggrad<N, LC, true> to rounding (tests/test_gpu_parity_segmented.py).
+// Steps that would need more than SEG_MMAX orders or sub-stepping are detected by A2' on the
+// device (SegArgs::notfast); then C2' returns at once and the general Hermitian kernel, launched
+// right behind it with run_if = notfast, does the work.
+#pragma once
+#include "small_seg.cuh"
+
+// theta <= SYM_TH[m]  <=>  theta^m / m! <= 2e-17 (vec_plan's criterion), m = 2..8
+__constant__ double c_sym_th[SEG_MMAX + 1] = {0.0, 0.0, 6.324548995781438e-09, 4.932419216236795e-06,
+                                              0.00014801641288189615, 0.001191356706809193, 0.004932419216236793,
+                                              0.013910766804023767, 0.030783527232167155};
+
+struct KappaTable {
+    double v[SEG_MMAX + 1][SEG_MMAX];
+    constexpr KappaTable() : v() {
+        double fact[SEG_MMAX + 1] = {};
+        fact[0] = 1.0;
+        for (int j = 1; j <= SEG_MMAX; ++j) fact[j] = fact[j - 1] * (double)j;
+        for (int a = 0; a <= SEG_MMAX; ++a)
+            for (int b = 0; b < SEG_MMAX; ++b) v[a][b] = 1.0 / ((double)(a + b + 1) * fact[a] * fact[b]);
+    }
+};
+__constant__ KappaTable c_kappa = KappaTable();
+
+// C = A*B, real N x N row-major in registers
+template <int N>
+GB_D void rm_mm(double (&C)[N * N], const double (&A)[N * N], const double (&B)[N * N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc = fma(A[i * N + k], B[k * N + j], acc);
+            C[i * N + j] = acc;
+        }
+}
+// y = A x, A real, x complex
+template <int N>
+GB_D void rm_mv(cplx (&y)[N], const double (&A)[N * N], const cplx (&x)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        cplx acc = mk(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < N; ++q) cfmar(acc, A[i * N + q], x[q]);
+        y[i] = acc;
+    }
+}
+// i^r w  (r = 0..3): swaps and sign flips only
+GB_D cplx rot_i(cplx w, int r) {
+    switch (r & 3) {
+        case 0: return w;
+        case 1: return mk(-w.y, w.x);
+        case 2: return mk(-w.x, -w.y);
+        default: return mk(w.y, -w.x);
+    }
+}
+
+// Hs (unscaled: H0 + sum_l a_l Hc_l of generator g at step n) and its 1-norm
+template <int N>
+GB_D double sym_form_H(const DevP& p, const SegArgs& a, int g, int n, double (&Hs)[N * N]) {
+    constexpr int NN = N * N;
+    const int G = p.G, NT = p.NT;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Hs[c] = __ldg(&a.H0r[(size_t)c * G + g]);
+    for (int l = 0; l < p.L; ++l) {
+        double am = p.eps[l * NT + n];
+        if (p.shape) am *= p.shape[l * NT + n];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Hs[c] = fma(am, __ldg(&a.Hcr[((size_t)l * NN + c) * G + g]), Hs[c]);
+    }
+    double nrm = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
+        nrm = fmax(nrm, s);
+    }
+    return nrm;
+}
+
+// ---------------------------------------------------------------------------
+// A2': segment propagators, thread per (g, seg)
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) small_formseg_sym(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int G = p.G, NT = p.NT;
+    if (idx >= (long long)G * a.NSEG) return;
+    const int g = (int)(idx % G), seg = (int)(idx / G);
+    const int n0 = seg * a.S, n1 = min(NT, n0 + a.S);
+    double Pr[NN], Pi[NN];
+    for (int n = n0; n < n1; ++n) {
+        const double dt = p.tlist[n + 1] - p.tlist[n];
+        double Hs[NN];
+        const double theta = dt * sym_form_H<N>(p, a, g, n, Hs);
+        if (theta > c_sym_th[SEG_MMAX]) *a.notfast = 1;   // the gradient kernel of this file cannot serve this step
+        int degree, s;
+        exp_plan(theta, degree, s);
+        const double sc = s > 0 ? dt * ldexp(1.0, -s) : dt;
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Hs[c] *= sc;
+        double Q[NN];
+        rm_mm<N>(Q, Hs, Hs);
+        // cos(Hs) = sum_j (-1)^j Q^j/(2j)!,  sin(Hs) = Hs sum_j (-1)^j Q^j/(2j+1)!,  j <= d2 = (degree-1)/2
+        const int d2 = (degree - 1) / 2;
+        double Cm[NN], Sp[NN];
+        {
+            const double sg = (d2 & 1) ? -1.0 : 1.0;
+            const double c1 = sg * c_invfact[2 * d2], c0 = -sg * c_invfact[2 * d2 - 2];
+            const double s1 = sg * c_invfact[2 * d2 + 1], s0 = -sg * c_invfact[2 * d2 - 1];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Cm[c] = c1 * Q[c]; Sp[c] = s1 * Q[c]; }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { Cm[i * N + i] += c0; Sp[i * N + i] += s0; }
+        }
+        for (int j = d2 - 2; j >= 0; --j) {
+            const double sg = (j & 1) ? -1.0 : 1.0;
+            const double cj = sg * c_invfact[2 * j], sj = sg * c_invfact[2 * j + 1];
+            double T1[NN], T2[NN];
+            rm_mm<N>(T1, Q, Cm);
+            rm_mm<N>(T2, Q, Sp);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Cm[c] = T1[c]; Sp[c] = T2[c]; }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { Cm[i * N + i] += cj; Sp[i * N + i] += sj; }
+        }
+        double Sm[NN];
+        rm_mm<N>(Sm, Hs, Sp);
+        for (int t = 0; t < s; ++t) {   // (C - iS)^2 = (C^2 - S^2) - i (2 S C)
+            double T1[NN], T2[NN], T3[NN];
+            rm_mm<N>(T1, Cm, Cm);
+            rm_mm<N>(T2, Sm, Sm);
+            rm_mm<N>(T3, Sm, Cm);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Cm[c] = T1[c] - T2[c]; Sm[c] = 2.0 * T3[c]; }
+        }
+        if (n == n0) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
+        } else {   // (C - iS)(Pr + i Pi)
+            double Tr[NN], Ti[NN];
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double ar = 0.0, ai = 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        ar = fma(Cm[i * N + k], Pr[k * N + j], ar);
+                        ar = fma(Sm[i * N + k], Pi[k * N + j], ar);
+                        ai = fma(Cm[i * N + k], Pi[k * N + j], ai);
+                        ai = fma(-Sm[i * N + k], Pr[k * N + j], ai);
+                    }
+                    Tr[i * N + j] = ar;
+                    Ti[i * N + j] = ai;
+                }
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Tr[c]; Pi[c] = Ti[c]; }
+        }
+    }
+    cplx* o = a.Pseg + (size_t)seg * NN * G + g;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) o[(size_t)c * G] = mk(Pr[c], Pi[c]);
+}
+
+// ---------------------------------------------------------------------------
+// C2': one backward step with M Taylor orders. Hs = dt H (real). On exit psi, chi hold the
+// start-of-step states and IM = Im sum_{a+b<=M-1} bt_a ch_b^dagger/(a+b+1).
+// ---------------------------------------------------------------------------
+template <int N, int M>
+GB_D void sym_step(const double (&Hs)[N * N], cplx (&psi)[N], cplx (&chi)[N], double (&IM)[N * N]) {
+    cplx e[M][N];
+    cplx w[N], ap[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { w[i] = psi[i]; ap[i] = psi[i]; }
+#pragma unroll
+    for (int b = 0; b < M; ++b)
+#pragma unroll
+        for (int i = 0; i < N; ++i) e[b][i] = cscale(w[i], c_kappa.v[0][b]);
+#pragma unroll
+    for (int aa = 1; aa <= M; ++aa) {
+        cplx nw[N];
+        rm_mv<N>(nw, Hs, w);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            w[i] = nw[i];
+            cfmar(ap[i], c_invfact[aa], rot_i(nw[i], aa));
+        }
+#pragma unroll
+        for (int b = 0; b < M - aa; ++b)
+#pragma unroll
+            for (int i = 0; i < N; ++i) cfmar(e[b][i], c_kappa.v[aa][b], rot_i(nw[i], aa));
+    }
+    cplx x[N], ac[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x[i] = chi[i]; ac[i] = chi[i]; }
+#pragma unroll
+    for (int c = 0; c < N * N; ++c) IM[c] = 0.0;
+#pragma unroll
+    for (int b = 0; b < M; ++b) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            const cplx z = rot_i(x[q], b);   // Im(e conj(z)) = e.y z.x - e.x z.y
+#pragma unroll
+            for (int pp = 0; pp < N; ++pp) {
+                double t = IM[pp * N + q];
+                t = fma(e[b][pp].y, z.x, t);
+                t = fma(-e[b][pp].x, z.y, t);
+                IM[pp * N + q] = t;
+            }
+        }
+        cplx nx[N];
+        rm_mv<N>(nx, Hs, x);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            x[i] = nx[i];
+            cfmar(ac[i], c_invfact[b + 1], rot_i(nx[i], b + 1));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) { psi[i] = ap[i]; chi[i] = ac[i]; }
+}
+
+// MINB = resident CTAs per SM the register allocation aims at (2: 255 registers, no spills; 3: 168 registers)
+template <int N, int MINB>
+__global__ void __launch_bounds__(128, MINB) small_seggrad_sym(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    if (*a.notfast) return;   // uniform over the grid: small_seggrad<N, LC, true> serves this call
+    const int K = p.K, G = p.G, NT = p.NT;
+    const int lane = threadIdx.x & 31;
+    const int BKL = a.BKL, SPW = 32 / BKL;
+    const int KGR = (K + BKL - 1) / BKL;
+    const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int SGR = (a.NSEG + SPW - 1) / SPW;
+    if (wid >= (long long)KGR * SGR) return;
+    const int kg = (int)(wid % KGR), sg = (int)(wid / KGR);
+    const int tk = lane % BKL, ts = lane / BKL;
+    const int k = kg * BKL + tk, seg = sg * SPW + ts;
+    const bool live = (k < K) && (seg < a.NSEG);
+    const int kk = k < K ? k : K - 1;
+    const int sseg = seg < a.NSEG ? seg : a.NSEG - 1;
+    const int n0 = sseg * a.S, n1 = min(NT, n0 + a.S);
+    const int g = p.gen[kk];
+    const double rho = p.rho[kk];
+
+    cplx chi[N], psi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        chi[i] = a.chiE[((size_t)sseg * N + i) * K + kk];
+        psi[i] = ld_cs(&p.psi[((size_t)n1 * N + i) * K + kk]);   // segment boundary written by the forward chain
+    }
+    for (int st = 0; st < a.S; ++st) {   // uniform trip count across the warp
+        const int n = n1 - 1 - st;
+        const bool act = live && n >= n0;
+        const int nn = n >= n0 ? n : n0;
+        const double dt = p.tlist[nn + 1] - p.tlist[nn];
+        double Hs[NN];
+        const double theta = dt * sym_form_H<N>(p, a, g, nn, Hs);
+        int m = 2;
+#pragma unroll
+        for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;
+        m = __reduce_max_sync(0xffffffffu, m);   // more orders never hurt: one uniform branch per warp
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Hs[c] *= dt;
+        double IM[NN];
+        switch (m) {
+            case 2: sym_step<N, 2>(Hs, psi, chi, IM); break;
+            case 3: sym_step<N, 3>(Hs, psi, chi, IM); break;
+            case 4: sym_step<N, 4>(Hs, psi, chi, IM); break;
+            case 5: sym_step<N, 5>(Hs, psi, chi, IM); break;
+            case 6: sym_step<N, 6>(Hs, psi, chi, IM); break;
+            case 7: sym_step<N, 7>(Hs, psi, chi, IM); break;
+            default: sym_step<N, 8>(Hs, psi, chi, IM); break;
+        }
+        for (int l = 0; l < p.L; ++l) {
+            double sl = dt * rho;
+            if (p.shape) sl *= p.shape[l * NT + nn];
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < NN; ++c) acc = fma(__ldg(&a.Hcr[((size_t)l * NN + c) * G + g]), IM[c], acc);
+            double red = act ? sl * acc : 0.0;
+            // fixed-order sum over the BKL trajectories of this lane group
+            for (int off = BKL >> 1; off > 0; off >>= 1) red += __shfl_down_sync(0xffffffffu, red, off, BKL);
+            if (tk == 0 && seg < a.NSEG && n >= n0) p.partial[(size_t)kg * p.L * NT + (size_t)l * NT + n] = red;
+        }
+    }
+}

@@ -186,6 +186,13 @@ class GrapeEngine:
             self._check(-rc)
         return rc
 
+    def small_schedule(self):
+        """0: not the segmented small path, 1: general, 2: Hermitian, 3: real-symmetric schedule served the last gradient."""
+        rc = int(self.lib.grape_b200_small_schedule(self._h))
+        if rc < 0:
+            self._check(-rc)
+        return rc
+
     def eval_fg_device(self, d_pulsevals_ptr, d_G_ptr=None, d_J_ptr=None):
         self._check(self.lib.grape_b200_eval_fg_device(self._h, d_pulsevals_ptr, d_G_ptr, d_J_ptr))
 

@@ -50,7 +50,29 @@ def _plans(p, eps, sample=64):
     return nrm
 
 
-def executed_flops_per_unit(p, eps, sample=64):
+def _sym_flops_per_unit(p, eps, sample=64):
+    """real-symmetric schedule (csrc/small_sym.cuh): real N x N products (2 N^3 flops) for cos / sin of Hs and four of
+    them for P_seg <- U_n P_seg; real-matrix x complex-vector Krylov chains (4 N^2 per order and state), the
+    e_b combination, Im M only, one real trace per control."""
+    N, L, NT, K, G = p.N, p.L, p.NT, p.K, p.G
+    nrm = _plans(p, eps, sample)
+    deg, s = _exp_plan(nrm)
+    d2 = (deg - 1) // 2
+    a_flops = (np.mean((2 + 2 * (d2 - 1) + 3 * s) * 2.0 * N ** 3) + 4 * 2.0 * N ** 3 + 2.0 * L * N * N) * G / K
+    m, _ = _vec_terms(nrm)
+    m = np.minimum(m, 8).astype(float)
+    c_flops = np.mean(12.0 * N * N * m + 10.0 * N * m + 2.0 * N * m * (m - 1)) + 4.0 * L * N * N + N * N
+    return float(a_flops + 8.0 * N * N + c_flops)
+
+
+def executed_flops_per_unit(p, eps, sample=64, schedule=None):
+    """schedule = GrapeEngine.small_schedule() of the measured call (3: real-symmetric kernels)."""
+    if schedule == 3:
+        return _sym_flops_per_unit(p, eps, sample)
+    return _general_flops_per_unit(p, eps, sample)
+
+
+def _general_flops_per_unit(p, eps, sample=64):
     """FP64 flops per (trajectory, step) unit that the small-N / sub-warp kernels execute
     (complex FMA = 8 flops, real-times-complex FMA = 4), following the kernels' own plans:
     propagator formation by Paterson-Stockmeyer Taylor + segment product (per generator-step,

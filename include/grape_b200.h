@@ -201,6 +201,13 @@ int64_t grape_b200_launch_count(const grape_b200_handle* h);
  * Both evaluate the same truncated series of the reference's GradGenerator step
  * (src/optimize.jl:880-896, docs/src/background.md:447-494). Negative: error code. */
 int grape_b200_gradient_form(grape_b200_handle* h);
+/* Which schedule of the small path (N <= 4) served the last gradient call (instrumentation; synchronises):
+ *   0 = not the time-segmented small path (plain chains, sub-warp or dense path),
+ *   1 = time-segmented, general generators (forward states read back from fw_storage),
+ *   2 = time-segmented, Hermitian generators (forward states recomputed backwards next to chi),
+ *   3 = time-segmented, real-symmetric generators (same as 2 in real matrix arithmetic, csrc/small_sym.cuh).
+ * All evaluate src/optimize.jl:824-1014 with the same truncation. Negative: error code. */
+int grape_b200_small_schedule(grape_b200_handle* h);
 
 #ifdef __cplusplus
 }

@@ -190,35 +190,6 @@ int small_setup(H* h, const grape_b200_problem* d) {
         SegArgs& a = h->seg;
         a.BKL = 1;
         while (a.BKL < K && a.BKL < 32) a.BKL <<= 1;
-        int S = (int)std::ceil(std::sqrt((double)NT));
-        {
-            // GPU-filling ensembles: the two heavy kernels (formseg, seggrad: 255 registers, 8 resident warps per
-            // SM) run in whole waves of warps, each wave taking S steps, while the boundary chains take NSEG steps
-            // of about a quarter of that cost: pick the segment length that minimises waves*S + NSEG/4.
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-            const long long resident = (long long)sms * 8;
-            const long long KGR = (K + a.BKL - 1) / a.BKL, SPW = 32 / a.BKL;
-            auto cost = [&](int s_, bool& full) {
-                const long long nseg = (NT + s_ - 1) / s_;
-                const long long warps = KGR * ((nseg + SPW - 1) / SPW);
-                full = warps >= resident;
-                return (double)((warps + resident - 1) / resident) * s_ + 0.26 * (double)nseg;
-            };
-            bool full = false;
-            double best = cost(S, full);
-            if (full) {
-                const int S0 = S;
-                for (int s_ = std::max(2, S0 / 2); s_ <= std::min(64, 2 * S0); ++s_) {
-                    bool f2;
-                    const double c = cost(s_, f2);
-                    if (f2 && c < best - 1e-9) { best = c; S = s_; }
-                }
-            }
-        }
-        if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
-        a.S = S < 2 ? 2 : (S > 64 ? 64 : S);
-        a.NSEG = (NT + a.S - 1) / a.S;
         {
             // Hermitian generators (the usual closed-system case): exp(-iH dt) is unitary and the forward state can be
             // carried backwards next to chi. Exact test on the caller's matrices; GRAPE_B200_SEG_HERM=0 disables.
@@ -266,6 +237,35 @@ int small_setup(H* h, const grape_b200_problem* d) {
                 CUDA_TRY(h, cudaMemset(a.notfast, 0, sizeof(int)));
             }
         }
+        int S = (int)std::ceil(std::sqrt((double)NT));
+        {
+            // GPU-filling ensembles: the two heavy kernels (formseg, seggrad: 255 registers, 8 resident warps per
+            // SM; 12 for the real-symmetric kernels) run in whole waves of warps, each wave taking S steps, while the boundary chains take NSEG steps
+            // of about a quarter of that cost: pick the segment length that minimises waves*S + NSEG/4.
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+            const long long resident = (long long)sms * (h->seg_real ? 12 : 8);   // small_sym.cuh kernels: 168 registers
+            const long long KGR = (K + a.BKL - 1) / a.BKL, SPW = 32 / a.BKL;
+            auto cost = [&](int s_, bool& full) {
+                const long long nseg = (NT + s_ - 1) / s_;
+                const long long warps = KGR * ((nseg + SPW - 1) / SPW);
+                full = warps >= resident;
+                return (double)((warps + resident - 1) / resident) * s_ + 0.26 * (double)nseg;
+            };
+            bool full = false;
+            double best = cost(S, full);
+            if (full) {
+                const int S0 = S;
+                for (int s_ = std::max(2, S0 / 2); s_ <= std::min(128, 4 * S0); ++s_) {
+                    bool f2;
+                    const double c = cost(s_, f2);
+                    if (f2 && c < best - 1e-9) { best = c; S = s_; }
+                }
+            }
+        }
+        if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
+        a.S = S < 2 ? 2 : (S > 128 ? 128 : S);
+        a.NSEG = (NT + a.S - 1) / a.S;
         // enough (generator, segment) pairs to fill the GPU: one thread forms the propagators of its segment and their
         // product; GRAPE_B200_NO_FORMSEG=1 / GRAPE_B200_FORCE_FORMSEG=1 override the size rule (tests)
         h->seg_fuse = (long long)G * a.NSEG >= 32768;
@@ -752,6 +752,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
             if (!rc) rc = dense2_setup(h->dense2, h->dense, p, h->dev_allocs, e);
             if (!rc && !h->dense2.on && !h->dense.strip_ok) { e = h->dense.strip_err; rc = GRAPE_B200_EINVAL; }
             if (!rc) rc = kry_setup(h->dense, h->dense2, p, h->dev_allocs, e);
+            if (!rc) rc = dense_dual_setup(h->dense, p, h->dense2.on, h->dev_allocs, e);
             if (rc) h->err = e;
             break;
         }
@@ -1087,7 +1088,7 @@ int grape_b200_gradient_form(grape_b200_handle* h) {
         h->err = "CUDA error while reading the gradient form";
         return -GRAPE_B200_ECUDA;
     }
-    return ok ? 1 : 0;
+    return ok ? (h->dense.d.nstrip > 1 && !h->dense2.on ? 2 : 1) : 0;
 }
 
 int grape_b200_small_schedule(grape_b200_handle* h) {

@@ -60,6 +60,18 @@ struct DenseDev {
     int Np, Kp, Cb, RT, Pf, Pb, MS, CcapF, CcapB, nD;
     const int* kry_ok; // block-recursion backward kernels return at once if *kry_ok (nullptr: always run)
     int mu_smem;   // backward strip kernel keeps its 8 rows of every mu_l^dagger in shared memory
+    int nstrip;    // strip chain: Taylor terms per grid barrier (1; 2: strips of H_n, H_n^2; 3: + H_n^3; dense_dual_setup)
+    int nP3;       // (L+1)(L+2)(L+3)/6 symmetrised triple products
+    const double* PTf;  // [nP3][2][Np][Np]  sum over the distinct orderings of H_i H_j H_k, i <= j <= k (lexicographic)
+    const double* PTa;
+    int herm;      // every operator equals its adjoint (exact): backward chains read the forward generators
+    int nP;        // (L+1)(L+2)/2 pair products
+    const double* PPf;  // [nP][2][Np][Np]  H_i H_j + H_j H_i (i < j), H_i^2 (i == j), pair order (0,0),(0,1)..(0,L),(1,1)..(L,L)
+    const double* PPa;  // the same products of the adjoints
+    // pre-formed generators of the current pulses, written once per call by dense_preform (all steps in parallel) and
+    // prefetched strip by strip by the multi-term chain:  pre[n][2 nstrip][Np][Np] = {Re H_n, Im H_n, Re H_n^2, Im H_n^2, ..}
+    double* preF;       // forward (H_n); nullptr: the chain forms its strips itself
+    double* preA;       // backward (H_n^dagger); == preF for Hermitian generators
     const double* Hf;
     const double* Ha;
     const double* Dm;
@@ -80,10 +92,11 @@ struct DensePlan {
     size_t kry_smem;
     int gridF, gridB;
     size_t smemF, smemB;
+    size_t smemF2;        // dense_chain<BWD, NS >= 2>: further operator strips
     bool ready;
     bool strip_ok;        // the 8-row strip kernels of this file can run (N, K(L+1) small enough)
     std::string strip_err;
-    DensePlan() : kry_smem(0), gridF(0), gridB(0), smemF(0), smemB(0), ready(false), strip_ok(true) { memset(&kd, 0, sizeof kd); }
+    DensePlan() : kry_smem(0), gridF(0), gridB(0), smemF(0), smemB(0), smemF2(0), ready(false), strip_ok(true) { memset(&kd, 0, sizeof kd); }
 };
 
 GB_D void dmma884(double (&acc)[2], double a, double b) {
@@ -173,6 +186,80 @@ GB_D void dense_mma_slice(const double* __restrict__ Bre, const double* __restri
     }
 }
 
+// One 8-column group, NS >= 2 operand strips: acc[q] += B_q X with every X fragment loaded once (B_q = the CTA's rows
+// of H_n^(q+1): NS Taylor terms per grid barrier).  4 NS independent DMMA chains per warp (8 warps share the pipe, so
+// a chain is revisited every >= 128 issue clocks, above the ~100 clk latency of a dependent DMMA).
+// Bq[q] = strip q in shared memory (re plane, im plane at + 8 * bstride).
+template <int NS, int UK>
+GB_D void dense_mma_multi(const double* const (&Bq)[3], int bstride,
+                          const double* __restrict__ Xre, const double* __restrict__ Xim, int ldx, int col0,
+                          int kbeg, int kend, DAcc (&acc)[NS]) {
+    const int lane = threadIdx.x & 31;
+    const int lr = lane >> 2, lc = lane & 3;
+    for (int kb = kbeg; kb < kend; kb += 4 * UK) {
+        double are[UK], aim[UK];
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int k0 = kb + 4 * u;
+            if (k0 < kend) {
+                const size_t off = (size_t)(k0 + lc) * ldx + col0 + lr;
+                are[u] = __ldcg(&Xre[off]);
+                aim[u] = __ldcg(&Xim[off]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int k0 = kb + 4 * u;
+            if (k0 < kend) {
+                const int bo = lr * bstride + k0 + lc;
+                double br[NS], bi[NS];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) { br[q] = Bq[q][bo]; bi[q] = Bq[q][8 * bstride + bo]; }
+#pragma unroll
+                for (int q = 0; q < NS; ++q) dmma884(acc[q].p1, are[u], br[q]);
+#pragma unroll
+                for (int q = 0; q < NS; ++q) dmma884(acc[q].p2, aim[u], bi[q]);
+#pragma unroll
+                for (int q = 0; q < NS; ++q) dmma884(acc[q].q1, are[u], bi[q]);
+#pragma unroll
+                for (int q = 0; q < NS; ++q) dmma884(acc[q].q2, aim[u], br[q]);
+            }
+        }
+    }
+}
+
+// Cross-warp (k-split) reduction of NS results of one 8-column group: afterwards thread t < 64 holds ALL NS complex
+// results for row nrow = t / 8, column m = t % 8 (so that one thread adds the terms in a fixed order).
+template <int NS>
+GB_D void dense_reduce_all(double* __restrict__ red, DAcc (&acc)[NS], cplx (&res)[NS]) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        double* rr = red + (size_t)((w * NS + q) * 2) * 64;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            rr[(2 * lc + e) * 8 + lr] = acc[q].p1[e] - acc[q].p2[e];
+            rr[64 + (2 * lc + e) * 8 + lr] = acc[q].q1[e] + acc[q].q2[e];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            cplx r = mk(0.0, 0.0);
+#pragma unroll
+            for (int ww = 0; ww < DENSE_THREADS / 32; ++ww) {
+                const double* rr = red + (size_t)((ww * NS + q) * 2) * 64;
+                r.x += rr[threadIdx.x];
+                r.y += rr[64 + threadIdx.x];
+            }
+            res[q] = r;
+        }
+    }
+    __syncthreads();
+}
+
 // Cross-warp (k-split) reduction. After the call, thread t holds the complex result for
 // column group g = t/64, row nrow = (t%64)/8, column m = t%8 (valid if g < ng).
 template <int NG>
@@ -260,6 +347,123 @@ GB_D void dense_form_H(const DevP& p, const double* __restrict__ Hall, int Np, i
     }
 }
 
+// rows r0..r0+7 of  sum_q coef[q] mats[q]  (planar matrices, coef in shared memory) into shared memory
+GB_D void dense_form_comb(const double* __restrict__ mats, int nmat, const double* __restrict__ coef, int Np, int MS,
+                          int r0, double* __restrict__ Hs_re, double* __restrict__ Hs_im) {
+    const size_t plane = (size_t)Np * Np;
+    constexpr int U = 8;
+    const int tot = 8 * Np;
+    const double* __restrict__ row = mats + (size_t)r0 * Np;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += U * DENSE_THREADS) {
+        double hr[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) hr[u] = hi[u] = 0.0;
+        for (int q = 0; q < nmat; ++q) {
+            const double cq = coef[q];
+            const double* __restrict__ Hq = row + (size_t)q * 2 * plane;
+            double tr[U], ti[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * DENSE_THREADS;
+                tr[u] = e < tot ? __ldg(&Hq[e]) : 0.0;
+                ti[u] = e < tot ? __ldg(&Hq[plane + e]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                hr[u] = fma(cq, tr[u], hr[u]);
+                hi[u] = fma(cq, ti[u], hi[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * DENSE_THREADS;
+            if (e < tot) {
+                const int r = e / Np, k = e - r * Np;
+                Hs_re[r * MS + k] = hr[u];
+                Hs_im[r * MS + k] = hi[u];
+            }
+        }
+    }
+}
+
+// H_n, H_n^2 [and H_n^3] of EVERY time step of the current pulses (embarrassingly parallel, HBM-write bound): thread =
+// one matrix element, blockIdx.y = chunk of time steps; the (L+1) + (L+1)(L+2)/2 [+ (L+1)(L+2)(L+3)/6] source values
+// stay in registers over the chunk.  H_n^2 = sum_{i<=j} c_i c_j P_ij,  H_n^3 = sum_{i<=j<=k} c_i c_j c_k S_ijk.
+template <int L, int NS>
+__global__ void __launch_bounds__(256) dense_preform(DevP p, const double* __restrict__ Hall, const double* __restrict__ PP,
+                                                     const double* __restrict__ PT, double* __restrict__ out, int Np, int chunk) {
+    const size_t plane = (size_t)Np * Np;
+    const size_t e = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= plane) return;
+    constexpr int PM = (L + 1) * (L + 2) / 2, TM = NS >= 3 ? (L + 1) * (L + 2) * (L + 3) / 6 : 1;
+    double hr[L + 1], hi[L + 1], qr[PM], qi[PM], tr[TM], ti[TM];
+#pragma unroll
+    for (int q = 0; q <= L; ++q) { hr[q] = __ldg(&Hall[(size_t)q * 2 * plane + e]); hi[q] = __ldg(&Hall[(size_t)q * 2 * plane + plane + e]); }
+#pragma unroll
+    for (int q = 0; q < PM; ++q) { qr[q] = __ldg(&PP[(size_t)q * 2 * plane + e]); qi[q] = __ldg(&PP[(size_t)q * 2 * plane + plane + e]); }
+    if (NS >= 3) {
+#pragma unroll
+        for (int q = 0; q < TM; ++q) { tr[q] = __ldg(&PT[(size_t)q * 2 * plane + e]); ti[q] = __ldg(&PT[(size_t)q * 2 * plane + plane + e]); }
+    }
+    const int n0 = blockIdx.y * chunk, n1 = min(p.NT, n0 + chunk);
+    for (int n = n0; n < n1; ++n) {
+        double c[L + 1];
+        c[0] = 1.0;
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            double a = p.eps[l * p.NT + n];
+            if (p.shape) a *= p.shape[l * p.NT + n];
+            c[1 + l] = a;
+        }
+        double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0, cr = 0.0, ci = 0.0;
+#pragma unroll
+        for (int q = 0; q <= L; ++q) { ar = fma(c[q], hr[q], ar); ai = fma(c[q], hi[q], ai); }
+        int q = 0, q3 = 0;   // orders of dense_dual_setup: (0,0),(0,1)..(L,L) and (0,0,0),(0,0,1)..(L,L,L)
+#pragma unroll
+        for (int i = 0; i <= L; ++i)
+#pragma unroll
+            for (int j = i; j <= L; ++j, ++q) {
+                const double cc = c[i] * c[j];
+                br = fma(cc, qr[q], br);
+                bi = fma(cc, qi[q], bi);
+                if (NS >= 3) {
+#pragma unroll
+                    for (int k = j; k <= L; ++k, ++q3) {
+                        const double c3 = cc * c[k];
+                        cr = fma(c3, tr[q3], cr);
+                        ci = fma(c3, ti[q3], ci);
+                    }
+                }
+            }
+        double* o = out + (size_t)n * (2 * NS) * plane + e;
+        __stcs(&o[0], ar);
+        __stcs(&o[plane], ai);
+        __stcs(&o[2 * plane], br);
+        __stcs(&o[3 * plane], bi);
+        if (NS >= 3) {
+            __stcs(&o[4 * plane], cr);
+            __stcs(&o[5 * plane], ci);
+        }
+    }
+}
+
+// cp.async of the 2 NS 8-row strips {Re H, Im H, Re H^2, Im H^2, ..} of step n into shared memory (row stride MS):
+// strip 0 at Hs (re, im), strips 1.. at HX
+template <int NS>
+GB_D void dense_prefetch_strips(const double* __restrict__ pre, int n, int Np, int MS, int r0,
+                                double* __restrict__ Hs, double* __restrict__ HX) {
+    const size_t plane = (size_t)Np * Np;
+    const double* src = pre + (size_t)n * (2 * NS) * plane + (size_t)r0 * Np;
+    const int segs = Np / 2;                 // 16-byte segments per row
+    const int tot = 2 * NS * 8 * segs;
+    for (int e = threadIdx.x; e < tot; e += DENSE_THREADS) {
+        const int sg = e % segs, r = (e / segs) & 7, q = e / (8 * segs);   // q = plane index 0 .. 2 NS - 1
+        double* dst = (q < 2 ? Hs + q * 8 * MS : HX + (q - 2) * 8 * MS) + r * MS + 2 * sg;
+        cp_async16(dst, src + (size_t)q * plane + (size_t)r * Np + 2 * sg);
+    }
+    cp_async_commit();
+}
+
 // ---------------------------------------------------------------------------
 // Chain kernel: forward sweep (BWD = false; reference src/optimize.jl:720-751) and the chi chain of the
 // Krylov-form backward (BWD = true; chi <- exp(+i H^dagger dt) chi going down in n, plus the running-cost
@@ -267,7 +471,13 @@ GB_D void dense_form_H(const DevP& p, const double* __restrict__ Hall, int Np, i
 // When the step qualifies for the Krylov form (s == 0, m <= MT) every Taylor term goes to its own HBM slot
 // (FT / BT) instead of the T0/T1 ping-pong, at no extra traffic.
 // ---------------------------------------------------------------------------
-template <bool BWD>
+// NS >= 2: further strips hold the same 8 rows of H_n^2 (and H_n^3); H_n^2 = sum_{i<=j} c_i c_j P_ij (c = (1, a_1 .. a_L), P_ij precomputed
+// once per handle), and every grid barrier of a Krylov-form step separates NS Taylor terms,
+//   T_{j+q} = (-+i dt)^q / ((j+1)..(j+q)) H^q T_j,   q = 1..NS,
+// computed from the same operand fragments: ceil(m/NS) instead of m dependent stages per step.  With the pre-formed
+// generators (DenseDev::preF / preA; required for NS = 3) the strips of step n+1 are fetched by cp.async behind the
+// last stage of step n.
+template <bool BWD, int NS>
 __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev d, KryDev kd) {
     if (BWD && !(*kd.ok)) return;   // uniform over the grid
     extern __shared__ __align__(16) double dsm[];
@@ -289,6 +499,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
     double* acc_im = acc_re + 8 * Ccap;
     double* red = acc_im + 8 * Ccap;
     double* jb_s = red + (DENSE_THREADS / 32) * DENSE_CGP * 128;
+    double* coef = jb_s + Ccap + 8;                 // NS >= 2: pair coefficients c_i c_j of the current step (<= 64)
+    double* HX = coef + 64;                         // NS >= 2: rows of H_n^2 [, H_n^3], 16 MS doubles each
+    constexpr bool DUAL = NS >= 2;
+    const double* const Bq[3] = {Hs_re, HX, HX + 16 * MS};
     const size_t splane = (size_t)Np * Kp;
     const int w = threadIdx.x >> 5;
     const int kslice = Np / 8, kbeg = w * kslice, kend = kbeg + kslice;
@@ -344,6 +558,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
         }
     };
 
+    const double* pre = DUAL ? (BWD ? d.preA : d.preF) : nullptr;
+    if (DUAL && pre) dense_prefetch_strips<NS>(pre, BWD ? NT - 1 : 0, Np, MS, r0, Hs_re, HX);
     for (int it = 0; it < NT; ++it) {
         const int n = BWD ? NT - 1 - it : it;
         const double dt = p.tlist[n + 1] - p.tlist[n];
@@ -351,17 +567,112 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
             const double wgt = n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]);
             gb_point(wgt);
         }
-        dense_form_H(p, Hall, Np, MS, r0, n, Hs_re, Hs_im);
+        if (DUAL && pre) cp_async_wait<0>();   // strips of this step: issued behind the previous step's last stage
+        else dense_form_H(p, Hall, Np, MS, r0, n, Hs_re, Hs_im);
         int m, s;
         dense_plan(p, d, n, dt, m, s);
         if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
         const bool kry = kd.on && s == 0 && m <= kd.MT;
         double* slots = kry ? terms + (size_t)n * kd.MT * 2 * splane : nullptr;
+        const bool dual = DUAL && kry && m >= 2;
+        if (DUAL && dual && !pre) {   // uniform over the grid
+            // c = (1, a_1 .. a_L); pair (i, j), i <= j, at index i (L+1) - i (i-1)/2 + (j - i)
+            if (threadIdx.x < d.nP) {
+                int i = 0, q = threadIdx.x;
+                while (q >= p.L + 1 - i) { q -= p.L + 1 - i; ++i; }
+                const int jj = i + q;
+                auto cf = [&](int t) {
+                    if (t == 0) return 1.0;
+                    double a = p.eps[(t - 1) * p.NT + n];
+                    if (p.shape) a *= p.shape[(t - 1) * p.NT + n];
+                    return a;
+                };
+                coef[threadIdx.x] = cf(i) * cf(jj);
+            }
+            __syncthreads();
+            dense_form_comb(BWD ? d.PPa : d.PPf, d.nP, coef, Np, MS, r0, HX, HX + 8 * MS);
+        }
         __syncthreads();
         const int nsub = 1 << s;
         const double dts = dt / nsub;
         for (int sub = 0; sub < nsub; ++sub) {
+            if (DUAL && dual) {
+                // NS Taylor terms per stage (nsub == 1 here): T_{j+q} = f_q H^q T_j, f_q = (-+i dts)^q / ((j+1)..(j+q))
+                for (int j = 0; j < m; j += NS) {
+                    const int nt = min(NS, m - j);   // terms of this stage
+                    const double* src = j == 0 ? state : slots + (size_t)j * 2 * splane;
+                    double xq[NS];
+                    {
+                        double x = 1.0;
+#pragma unroll
+                        for (int q = 0; q < NS; ++q) { x *= dts / (j + q + 1); xq[q] = x; }
+                    }
+                    // f_q res: q = 0: (-+i) x res; q = 1: -x res; q = 2: (+-i) x res   (forward: -i, backward: +i)
+                    auto term = [&](int q, double x, cplx r, double& tr, double& ti) {
+                        if (q == 0) { tr = BWD ? -x * r.y : x * r.y; ti = BWD ? x * r.x : -x * r.x; }
+                        else if (q == 1) { tr = -x * r.x; ti = -x * r.y; }
+                        else { tr = BWD ? x * r.y : -x * r.y; ti = BWD ? -x * r.x : x * r.x; }
+                    };
+                    for (int pg = cg0; pg < cg1; pg += DENSE_CGP) {
+                        const int ng = min(DENSE_CGP, cg1 - pg);
+                        const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
+                        if (ng == 1 && nt == NS) {
+                            DAcc acc[NS];
+#pragma unroll
+                            for (int q = 0; q < NS; ++q) acc[q].zero();
+                            dense_mma_multi<NS, 8>(Bq, MS, src, src + splane, Kp, pg * 8, kbeg, kend, acc);
+                            cplx res[NS];
+                            dense_reduce_all<NS>(red, acc, res);   // threads 0..63 hold all NS results
+                            if (threadIdx.x < 64) {
+                                const int cglob = pg * 8 + mc;
+                                const size_t off = (size_t)(r0 + nrow) * Kp + cglob;
+                                double ar = acc_re[nrow * Ccap + cglob - cbeg], ai = acc_im[nrow * Ccap + cglob - cbeg];
+#pragma unroll
+                                for (int q = 0; q < NS; ++q) {   // fixed summation order: term j+1, j+2, ..
+                                    double tr, ti;
+                                    term(q, xq[q], res[q], tr, ti);
+                                    if (j + q + 1 < m) {
+                                        double* dst = slots + (size_t)(j + q + 1) * 2 * splane;
+                                        dst[off] = tr;
+                                        dst[splane + off] = ti;
+                                    }
+                                    ar += tr;
+                                    ai += ti;
+                                }
+                                acc_re[nrow * Ccap + cglob - cbeg] = ar;
+                                acc_im[nrow * Ccap + cglob - cbeg] = ai;
+                            }
+                        } else {
+                            // several column groups per CTA (or a short last stage): one pass per strip
+                            for (int q = 0; q < nt; ++q) {
+                                int col0[DENSE_CGP];
+                                DAcc acc[DENSE_CGP];
+#pragma unroll
+                                for (int gg = 0; gg < DENSE_CGP; ++gg) { col0[gg] = (pg + gg) * 8; acc[gg].zero(); }
+                                dense_mma_slice<DENSE_CGP, true, 2>(Bq[q], Bq[q] + 8 * MS, MS, 1.0, src, src + splane, Kp, col0, ng,
+                                                                    kbeg, kend, acc);
+                                const cplx res = dense_reduce<DENSE_CGP>(red, acc, ng);
+                                if (g < ng) {
+                                    const int cglob = (pg + g) * 8 + mc;
+                                    const size_t off = (size_t)(r0 + nrow) * Kp + cglob;
+                                    double tr, ti, x = 1.0;
+                                    for (int t = 0; t <= q; ++t) x *= dts / (j + t + 1);
+                                    term(q, x, res, tr, ti);
+                                    if (j + q + 1 < m) {
+                                        double* dst = slots + (size_t)(j + q + 1) * 2 * splane;
+                                        dst[off] = tr;
+                                        dst[splane + off] = ti;
+                                    }
+                                    acc_re[nrow * Ccap + cglob - cbeg] += tr;
+                                    acc_im[nrow * Ccap + cglob - cbeg] += ti;
+                                }
+                            }
+                        }
+                    }
+                    if (j + NS < m) grid.sync();
+                }
+            } else
             for (int j = 1; j <= m; ++j) {
                 const double* src = j == 1 ? state : (kry ? slots + (size_t)(j - 1) * 2 * splane : ((j - 1) & 1 ? d.T1 : d.T0));
                 double* dst = kry ? slots + (size_t)j * 2 * splane : ((j & 1) ? d.T1 : d.T0);
@@ -401,6 +712,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
             }
             __syncthreads();
             const bool last = sub == nsub - 1;
+            if (DUAL && pre && last && it + 1 < NT)   // every warp is done with this step's strips: fetch the next ones
+                dense_prefetch_strips<NS>(pre, BWD ? n - 1 : n + 1, Np, MS, r0, Hs_re, HX);   // behind the epilogue and the barrier
             if (BWD && last && gb && n > 0) {
                 // chi += lambda_b * 0.5 (t_{n+1} - t_{n-1}) / rho * xi(Psi(t_{n-1})), xi = -D Psi  (optimize.jl:897-908)
                 const double* st = d.store + (size_t)n * 2 * splane;
@@ -830,6 +1143,7 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     int rc;
     if ((rc = upd(hf, &d.Hf))) return rc;
     if ((rc = upd(ha, &d.Ha))) return rc;
+    d.herm = (hf == ha) ? 1 : 0;
     if (p.gb_kind) {
         std::vector<double> dm(2 * hplane, 0.0);
         for (int i = 0; i < N; ++i)
@@ -874,8 +1188,8 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     }
     if (dp.smemF > 227 * 1024 || dp.smemB > 227 * 1024) { dp.strip_ok = false; dp.strip_err = "dense strip kernels: shared-memory tile does not fit (N or K*(L+1) too large)"; }
     if (dp.strip_ok) {
-        cudaError_t e = cudaFuncSetAttribute(dense_chain<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_chain<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        cudaError_t e = cudaFuncSetAttribute(dense_chain<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_chain<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemB);
         if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e); return GRAPE_B200_ECUDA; }
     }
@@ -886,6 +1200,145 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     return 0;
 }
 
+// C (+)= A B (+ B A if sym): planar complex Np x Np, one thread per output element (set-up only)
+__global__ void __launch_bounds__(256) dense_pair_product(const double* __restrict__ A, const double* __restrict__ B,
+                                                          double* __restrict__ C, int Np, int sym, int accum) {
+    const size_t plane = (size_t)Np * Np;
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), i = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (i >= Np || j >= Np) return;
+    double cr = accum ? C[(size_t)i * Np + j] : 0.0, ci = accum ? C[plane + (size_t)i * Np + j] : 0.0;
+    for (int k = 0; k < Np; ++k) {
+        const double ar = A[(size_t)i * Np + k], ai = A[plane + (size_t)i * Np + k];
+        const double br = B[(size_t)k * Np + j], bi = B[plane + (size_t)k * Np + j];
+        cr = fma(ar, br, cr); cr = fma(-ai, bi, cr);
+        ci = fma(ar, bi, ci); ci = fma(ai, br, ci);
+        if (sym) {
+            const double xr = B[(size_t)i * Np + k], xi = B[plane + (size_t)i * Np + k];
+            const double yr = A[(size_t)k * Np + j], yi = A[plane + (size_t)k * Np + j];
+            cr = fma(xr, yr, cr); cr = fma(-xi, yi, cr);
+            ci = fma(xr, yi, ci); ci = fma(xi, yr, ci);
+        }
+    }
+    C[(size_t)i * Np + j] = cr;
+    C[plane + (size_t)i * Np + j] = ci;
+}
+
+// Several Taylor terms per grid barrier in the strip chains (dense_chain<BWD, NS>, NS = 2 or 3): needs the
+// Krylov-form term storage, at most 3 controls and room for NS operator strips in shared memory; NS = 3 also needs
+// the pre-formed generators (NT x 6 planes of device memory; x 2 for non-Hermitian generators).
+// GRAPE_B200_DENSE_TERMS=1|2|3 caps NS, GRAPE_B200_DENSE_PREFORM=0 makes the chain form its strips itself (NS <= 2).
+// Called after kry_setup.
+inline int dense_dual_setup(DensePlan& dp, const DevP& p, bool tiled_chains, std::vector<void*>& allocs, std::string& err) {
+    DenseDev& d = dp.d;
+    d.nstrip = 1;
+    d.preF = d.preA = nullptr;
+    int want = 3;
+    if (const char* env = getenv("GRAPE_B200_DENSE_TERMS")) want = atoi(env);
+    if (const char* env = getenv("GRAPE_B200_DENSE_DUAL")) { if (atoi(env) == 0) want = 1; }
+    if (want < 2 || !dp.kd.on || tiled_chains || !dp.strip_ok || p.L > 3) return 0;
+    const char* envp = getenv("GRAPE_B200_DENSE_PREFORM");
+    const bool allow_pre = !(envp && atoi(envp) == 0);
+    const size_t hplane = (size_t)d.Np * d.Np;
+    auto smem_of = [&](int ns) { return dp.smemF + sizeof(double) * (64 + (size_t)(ns - 1) * 16 * d.MS); };
+    int ns = std::min(want, 3);
+    if (ns == 3 && (smem_of(3) > 227 * 1024 || !allow_pre)) ns = 2;
+    if (smem_of(2) > 227 * 1024) return 0;
+    // pre-formed generators: NT x 2 ns planes
+    auto try_pre = [&](int nsx) -> bool {
+        const size_t bytes = sizeof(double) * (size_t)p.NT * 2 * nsx * hplane;
+        size_t freeB = 0, totB = 0;
+        if (cudaMemGetInfo(&freeB, &totB) != cudaSuccess) { cudaGetLastError(); return false; }
+        if ((double)bytes * (d.herm ? 1 : 2) > 0.6 * (double)freeB) return false;
+        double* a = nullptr;
+        double* b = nullptr;
+        if (cudaMalloc((void**)&a, bytes) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (d.herm) b = a;
+        else if (cudaMalloc((void**)&b, bytes) != cudaSuccess) { cudaGetLastError(); cudaFree(a); return false; }
+        allocs.push_back(a);
+        if (b != a) allocs.push_back(b);
+        d.preF = a; d.preA = b;
+        return true;
+    };
+    if (allow_pre) {
+        if (ns == 3 && !try_pre(3)) ns = 2;
+        if (ns == 2 && !d.preF) try_pre(2);
+    }
+    // operator products (once per handle)
+    const int nP = (p.L + 1) * (p.L + 2) / 2, nP3 = (p.L + 1) * (p.L + 2) * (p.L + 3) / 6;
+    auto dalloc = [&](double** q, size_t n) -> bool {
+        if (cudaMalloc((void**)q, sizeof(double) * n) != cudaSuccess) { cudaGetLastError(); return false; }
+        allocs.push_back(*q);
+        return true;
+    };
+    double *pf = nullptr, *pa = nullptr, *tf = nullptr, *ta = nullptr, *tmp = nullptr;
+    if (!dalloc(&pf, (size_t)nP * 2 * hplane) || !dalloc(&pa, (size_t)nP * 2 * hplane)) return 0;
+    if (ns == 3 && (!dalloc(&tf, (size_t)nP3 * 2 * hplane) || !dalloc(&ta, (size_t)nP3 * 2 * hplane) || !dalloc(&tmp, 2 * hplane))) return 0;
+    dim3 grid((d.Np + 31) / 32, (d.Np + 7) / 8);
+    for (int side = 0; side < 2; ++side) {
+        const double* Hm = side ? d.Ha : d.Hf;
+        double* P = side ? pa : pf;
+        double* T = side ? ta : tf;
+        auto M = [&](int i) { return Hm + (size_t)i * 2 * hplane; };
+        int q = 0, q3 = 0;
+        for (int i = 0; i <= p.L; ++i)
+            for (int j = i; j <= p.L; ++j, ++q) {
+                dense_pair_product<<<grid, 256>>>(M(i), M(j), P + (size_t)q * 2 * hplane, d.Np, i != j, 0);
+                if (ns < 3) continue;
+                for (int k = j; k <= p.L; ++k, ++q3) {
+                    // sum over the distinct orderings (a, b, c) of (i, j, k) of H_a (H_b H_c)
+                    int perm[6][3] = {{i, j, k}, {i, k, j}, {j, i, k}, {j, k, i}, {k, i, j}, {k, j, i}};
+                    int done = 0;
+                    for (int t = 0; t < 6; ++t) {
+                        bool dup = false;
+                        for (int u = 0; u < t; ++u)
+                            if (perm[u][0] == perm[t][0] && perm[u][1] == perm[t][1] && perm[u][2] == perm[t][2]) dup = true;
+                        if (dup) continue;
+                        dense_pair_product<<<grid, 256>>>(M(perm[t][1]), M(perm[t][2]), tmp, d.Np, 0, 0);
+                        dense_pair_product<<<grid, 256>>>(M(perm[t][0]), tmp, T + (size_t)q3 * 2 * hplane, d.Np, 0, done ? 1 : 0);
+                        done = 1;
+                    }
+                }
+            }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) { err = std::string("operator products failed: ") + cudaGetErrorString(cudaGetLastError()); return GRAPE_B200_ECUDA; }
+    const size_t smem = smem_of(ns);
+    cudaError_t e = ns == 3 ? cudaFuncSetAttribute(dense_chain<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(dense_chain<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = ns == 3 ? cudaFuncSetAttribute(dense_chain<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : cudaFuncSetAttribute(dense_chain<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); d.preF = d.preA = nullptr; return 0; }
+    d.PPf = pf; d.PPa = pa; d.nP = nP; d.PTf = tf; d.PTa = ta; d.nP3 = nP3; d.nstrip = ns;
+    dp.smemF2 = smem;
+    return 0;
+}
+
+template <int L>
+inline void dense_preform_launch(const DenseDev& d, const DevP& p, bool adjoint, dim3 grid, int chunk, cudaStream_t st) {
+    const double* Hs_ = adjoint ? d.Ha : d.Hf;
+    const double* PP_ = adjoint ? d.PPa : d.PPf;
+    const double* PT_ = adjoint ? d.PTa : d.PTf;
+    double* out = adjoint ? d.preA : d.preF;
+    if (d.nstrip == 3) dense_preform<L, 3><<<grid, 256, 0, st>>>(p, Hs_, PP_, PT_, out, d.Np, chunk);
+    else dense_preform<L, 2><<<grid, 256, 0, st>>>(p, Hs_, PP_, PT_, out, d.Np, chunk);
+}
+inline void dense_run_preform(DensePlan& dp, const DevP& p, bool adjoint, cudaStream_t st, int64_t& launches) {
+    DenseDev& d = dp.d;
+    const int chunk = 32;
+    dim3 grid((unsigned)(((size_t)d.Np * d.Np + 255) / 256), (unsigned)((p.NT + chunk - 1) / chunk));
+    if (p.L == 1) dense_preform_launch<1>(d, p, adjoint, grid, chunk, st);
+    else if (p.L == 2) dense_preform_launch<2>(d, p, adjoint, grid, chunk, st);
+    else dense_preform_launch<3>(d, p, adjoint, grid, chunk, st);
+    launches++;
+}
+template <bool BWD>
+inline void dense_chain_launch(DensePlan& dp, void** args, cudaStream_t st) {
+    const DenseDev& d = dp.d;
+    if (d.nstrip == 3) cudaLaunchCooperativeKernel((void*)dense_chain<BWD, 3>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF2, st);
+    else if (d.nstrip == 2) cudaLaunchCooperativeKernel((void*)dense_chain<BWD, 2>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF2, st);
+    else cudaLaunchCooperativeKernel((void*)dense_chain<BWD, 1>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF, st);
+}
+
 inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int64_t& launches) {
     DenseDev& d = dp.d;
     const size_t splane = (size_t)d.Np * d.Kp;
@@ -893,7 +1346,8 @@ inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int
     cudaMemcpyAsync(d.store, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     DevP pp = p;
     void* args[] = {&pp, &d, &dp.kd};
-    cudaLaunchCooperativeKernel((void*)dense_chain<false>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF, st);
+    if (d.nstrip > 1 && d.preF) dense_run_preform(dp, p, false, st, launches);
+    dense_chain_launch<false>(dp, args, st);
     dense_tau<<<p.K, 256, 0, st>>>(p, d, dp.gridF);
     launches += 2;
 }
@@ -908,7 +1362,8 @@ inline void dense_run_backward(DensePlan& dp, const DevP& p, const cplx* chi_hos
     launches += 2;
     if (dp.kd.on) {
         void* cargs[] = {&pp, &d, &dp.kd};
-            cudaLaunchCooperativeKernel((void*)dense_chain<true>, dim3(dp.gridF), dim3(DENSE_THREADS), cargs, dp.smemF, st);
+        if (d.nstrip > 1 && d.preA && d.preA != d.preF) dense_run_preform(dp, p, true, st, launches);
+        dense_chain_launch<true>(dp, cargs, st);
         launches += 1;
     }
 }

@@ -180,7 +180,8 @@ class GrapeEngine:
         return int(self.lib.grape_b200_launch_count(self._h))
 
     def gradient_form(self):
-        """0: GradGenerator block recursion, 1: Krylov form (dense path) served the last gradient call."""
+        """0: GradGenerator block recursion, 1: Krylov form (dense path), 2: Krylov form with two Taylor terms per
+        grid barrier in the strip chains served the last gradient call."""
         rc = int(self.lib.grape_b200_gradient_form(self._h))
         if rc < 0:
             self._check(-rc)

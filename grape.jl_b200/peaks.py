@@ -123,6 +123,6 @@ def dense_flops_per_unit(p, eps, form=0):
     terms = float(np.mean(m * 2.0 ** sv))
     gbf = 8.0 * N * N if p.gb_kind else 0.0
     fwd = 8.0 * N * N * terms + gbf
-    if form == 1:
+    if form >= 1:
         return fwd, 8.0 * N * N * terms + gbf, 8.0 * N * N * float(np.mean(m)), terms
     return fwd, 8.0 * N * N * terms * (1 + 2 * L) + gbf, 0.0, terms

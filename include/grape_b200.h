@@ -198,6 +198,7 @@ int64_t grape_b200_launch_count(const grape_b200_handle* h);
  *   0 = GradGenerator block recursion (1+2L operator applications per Taylor order; the only form
  *       of the small / sub-warp paths' :taylor method, of sub-stepped steps and of gradient_method=:taylor),
  *   1 = Krylov form (dense path: chi chain on K columns + one DMMA contraction per step, csrc/dense_kry.cuh).
+ *   2 = Krylov form whose strip chains advance two Taylor terms per grid barrier (H_n and H_n^2 strips, csrc/dense.cuh).
  * Both evaluate the same truncated series of the reference's GradGenerator step
  * (src/optimize.jl:880-896, docs/src/background.md:447-494). Negative: error code. */
 int grape_b200_gradient_form(grape_b200_handle* h);

@@ -45,7 +45,7 @@ def _both_forms(p, eps, rtol=1e-10, **env):
             e = engine(p)
         G = np.zeros_like(eps)
         J = e.evaluate_gradient(G, eps)
-        assert e.gradient_form() == form, (kry, e.gradient_form())
+        assert (e.gradient_form() > 0) == bool(form), (kry, e.gradient_form())
         assert abs(J - ref["J"]) <= rtol * max(1.0, abs(ref["J"])), (J, ref["J"])
         assert np.max(np.abs(e.J_parts - ref["J_parts"])) <= rtol * max(1.0, np.max(np.abs(ref["J_parts"])))
         assert np.max(np.abs(e.tau_vals - ref["tau"])) <= rtol
@@ -117,7 +117,7 @@ def test_form_switches_per_call_on_one_handle(lib_built):
         ref = go.evaluate_gradient(op, x)
         G = np.zeros_like(x)
         J = e.evaluate_gradient(G, x)
-        assert e.gradient_form() == form
+        assert (e.gradient_form() > 0) == bool(form)
         assert abs(J - ref["J"]) <= 1e-9
         assert np.max(np.abs(G - ref["G"])) <= 1e-9 * max(np.max(np.abs(ref["G"])), 1e-6)
     e.close()
@@ -148,7 +148,7 @@ def test_split_forward_backward_and_host_chi(lib_built):
     sums = e.forward(eps)
     Gp = np.zeros_like(eps)
     e.backward(sums, Gp)
-    assert e.gradient_form() == 1
+    assert e.gradient_form() >= 1
     assert np.array_equal(Gp, G)
     e.close()
     ph, _ = configs.c4_dense450(N=50, K=7, NT=5)
@@ -160,7 +160,7 @@ def test_split_forward_backward_and_host_chi(lib_built):
     chiT = (np.sum(tau) / ph.K ** 2) * ph.tgt          # chi of J_T_sm, evaluated on the host
     Gh = np.zeros_like(eps)
     eh.backward_chi(chiT, Gh)
-    assert eh.gradient_form() == 1
+    assert eh.gradient_form() >= 1
     assert np.max(np.abs(Gh - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
     eh.close()
 
@@ -181,7 +181,7 @@ def test_c5_full_width_forms_agree(lib_built):
             e = engine(p)
         G = np.zeros_like(eps)
         J = e.evaluate_gradient(G, eps)
-        assert e.gradient_form() == kry
+        assert (e.gradient_form() > 0) == bool(kry)
         res.append((J, G))
         e.close()
     assert abs(res[0][0] - res[1][0]) <= 1e-12
@@ -200,8 +200,55 @@ def test_large_n_few_trajectories_uses_tiled_kernels(lib_built):
             e = engine(p)
         G = np.zeros_like(eps)
         J = e.evaluate_gradient(G, eps)
-        assert e.gradient_form() == kry
+        assert (e.gradient_form() > 0) == bool(kry)
         assert abs(J - ref["J"]) <= 1e-10
         assert np.max(np.abs(G - ref["G"])) <= 1e-10 * scale
         assert np.max(np.abs(e.final_states() - ref["final_states"])) <= 1e-12
         e.close()
+
+
+@pytest.mark.parametrize("N,K,NT,L", [(450, 24, 3, 2), (450, 16, 4, 2), (100, 16, 6, 3), (130, 9, 5, 1), (64, 40, 5, 2)])
+def test_two_terms_per_barrier_matches_single_term_chain(lib_built, N, K, NT, L):
+    """strip chains with strips of H_n^2 (and H_n^3): two / three Taylor terms per grid barrier (csrc/dense.cuh
+    dense_chain<BWD, NS>; one or several 8-column groups per CTA, Taylor orders of every residue mod NS, 1..3 controls)
+    against the one-term-per-barrier chain: same truncated series, so J and every gradient element agree to 1e-12"""
+    if L == 2:
+        p, eps = configs.c4_dense450(N=N, K=K, NT=NT)
+    else:
+        p, eps = configs.random_problem(K=K, N=N, L=L, NT=NT, G=1, seed=500 + N, hermitian=False, shaped=True)
+        p.tlist = p.tlist * (0.5 / np.sqrt(N))
+    res = []
+    # three / two Taylor terms per barrier with the generators of all steps pre-formed once per call (strips of H_n,
+    # H_n^2 [, H_n^3] prefetched by cp.async; the non-Hermitian cases keep a second set for the adjoints), two terms with
+    # the chain forming its strips itself, and the single-term chain
+    for terms, pre in ((3, 1), (2, 1), (2, 0), (1, 0)):
+        with _Env(GRAPE_B200_DENSE2=0, GRAPE_B200_DENSE_TERMS=terms, GRAPE_B200_DENSE_PREFORM=pre):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        for _ in range(2):                       # twice: the prefetch state must not leak between calls
+            J = e.evaluate_gradient(G, eps)
+        assert e.gradient_form() == (2 if terms > 1 else 1)
+        res.append((J, G.copy(), e.final_states(), e.stored_states(K - 1)))
+        e.close()
+    scale = np.max(np.abs(res[3][1]))
+    for r in res[:3]:
+        assert abs(r[0] - res[3][0]) <= 1e-12
+        assert np.max(np.abs(r[1] - res[3][1])) <= 1e-12 * scale
+        assert np.max(np.abs(r[2] - res[3][2])) <= 1e-13
+        assert np.max(np.abs(r[3] - res[3][3])) <= 1e-13
+    assert np.array_equal(res[1][1], res[2][1])   # same arithmetic, only the operand source differs
+
+
+def test_two_terms_per_barrier_full_width_oracle(lib_built):
+    """N = 450 with three 8-column groups on two column parts (1 and 2 groups per CTA): oracle parity of the dual chain
+    (:taylor oracle = N x N exponentials only; agrees with :gradgen to 1e-14, tests/test_oracle_known_answers.py)"""
+    p, eps = configs.c4_dense450(N=450, K=24, NT=2)
+    ref = go.evaluate_gradient(go.from_problem(p, gradient_method=go.TAYLOR), eps)
+    e = engine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    assert e.gradient_form() == 2
+    assert abs(J - ref["J"]) <= 1e-10
+    assert np.max(np.abs(G - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
+    assert np.max(np.abs(e.final_states() - ref["final_states"])) <= 1e-12
+    e.close()

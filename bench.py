@@ -120,8 +120,9 @@ def cpu_reference_run(p, eps, sample_k, sample_nt, steps, warmup):
         cores = os.cpu_count() or co.max_threads()
     sample_k = min(sample_k, p.K)
     sample_nt = min(sample_nt, p.NT)
-    for _ in range(warmup):
-        co.evaluate_gradient(p, eps, k_count=min(sample_k, 4 * cores), nt_count=min(sample_nt, 50), nthreads=cores)
+    if p.N <= 32:   # dense configs: one sample already takes minutes of core time, no separate warm-up
+        for _ in range(warmup):
+            co.evaluate_gradient(p, eps, k_count=min(sample_k, 4 * cores), nt_count=min(sample_nt, 50), nthreads=cores)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
@@ -136,7 +137,9 @@ def cpu_reference_run(p, eps, sample_k, sample_nt, steps, warmup):
 
 def cpu_sample_size(name):
     # sized for roughly 10-30 core-seconds of CPU work
-    return {"c1": (1, 500), "c2": (4, 2000), "c3": (1024, 1000), "c4": (16, 2), "c5": (16, 1)}[name]
+    # c4: ~30 core-seconds per unit (1350 x 1350 block exponential); c5: ~5 core-minutes per unit (3072 x 3072),
+    # so its sample is one trajectory-step per host thread, once
+    return {"c1": (1, 500), "c2": (4, 2000), "c3": (1024, 1000), "c4": (16, 1), "c5": (16, 1)}[name]
 
 
 # ---------------------------------------------------------------------------- main

@@ -753,6 +753,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
             if (!rc && !h->dense2.on && !h->dense.strip_ok) { e = h->dense.strip_err; rc = GRAPE_B200_EINVAL; }
             if (!rc) rc = kry_setup(h->dense, h->dense2, p, h->dev_allocs, e);
             if (!rc) rc = dense_dual_setup(h->dense, p, h->dense2.on, h->dev_allocs, e);
+            if (!rc) rc = dense2_multi_setup(h->dense2, h->dense, e);
             if (rc) h->err = e;
             break;
         }
@@ -917,7 +918,10 @@ int grape_b200_enqueue_combine(grape_b200_handle* h) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int blocks = (h->LNT + 255) / 256;
     combine_grad<<<blocks < 296 ? blocks : 296, 256, 0, h->stream>>>(h->p);
-    h->launches++;
+    // J_parts again, from the sums as they are NOW: for functionals whose chi does not couple the trajectories
+    // (J_T_re, J_T_ss) the caller may all-reduce sums[4] together with grad_J_Tb, i.e. after enqueue_backward
+    finalize_J<<<1, 256, 0, h->stream>>>(h->p);
+    h->launches += 2;
     return 0;
 }
 int grape_b200_finish(grape_b200_handle* h) {
@@ -1088,7 +1092,7 @@ int grape_b200_gradient_form(grape_b200_handle* h) {
         h->err = "CUDA error while reading the gradient form";
         return -GRAPE_B200_ECUDA;
     }
-    return ok ? (h->dense.d.nstrip > 1 && !h->dense2.on ? 2 : 1) : 0;
+    return ok ? (h->dense.d.nstrip > 1 ? 2 : 1) : 0;
 }
 
 int grape_b200_small_schedule(grape_b200_handle* h) {

@@ -1235,14 +1235,19 @@ inline int dense_dual_setup(DensePlan& dp, const DevP& p, bool tiled_chains, std
     int want = 3;
     if (const char* env = getenv("GRAPE_B200_DENSE_TERMS")) want = atoi(env);
     if (const char* env = getenv("GRAPE_B200_DENSE_DUAL")) { if (atoi(env) == 0) want = 1; }
-    if (want < 2 || !dp.kd.on || tiled_chains || !dp.strip_ok || p.L > 3) return 0;
+    if (want < 2 || !dp.kd.on || p.L > 3) return 0;
+    if (!tiled_chains && !dp.strip_ok) return 0;
     const char* envp = getenv("GRAPE_B200_DENSE_PREFORM");
     const bool allow_pre = !(envp && atoi(envp) == 0);
     const size_t hplane = (size_t)d.Np * d.Np;
     auto smem_of = [&](int ns) { return dp.smemF + sizeof(double) * (64 + (size_t)(ns - 1) * 16 * d.MS); };
     int ns = std::min(want, 3);
-    if (ns == 3 && (smem_of(3) > 227 * 1024 || !allow_pre)) ns = 2;
-    if (smem_of(2) > 227 * 1024) return 0;
+    if (tiled_chains) {
+        if (!allow_pre) return 0;   // the tiled multi-term chain (dense2_chain_multi) reads pre-formed generators only
+    } else {
+        if (ns == 3 && (smem_of(3) > 227 * 1024 || !allow_pre)) ns = 2;
+        if (smem_of(2) > 227 * 1024) return 0;
+    }
     // pre-formed generators: NT x 2 ns planes
     auto try_pre = [&](int nsx) -> bool {
         const size_t bytes = sizeof(double) * (size_t)p.NT * 2 * nsx * hplane;
@@ -1263,6 +1268,7 @@ inline int dense_dual_setup(DensePlan& dp, const DevP& p, bool tiled_chains, std
         if (ns == 3 && !try_pre(3)) ns = 2;
         if (ns == 2 && !d.preF) try_pre(2);
     }
+    if (tiled_chains && !d.preF) return 0;
     // operator products (once per handle)
     const int nP = (p.L + 1) * (p.L + 2) / 2, nP3 = (p.L + 1) * (p.L + 2) * (p.L + 3) / 6;
     auto dalloc = [&](double** q, size_t n) -> bool {
@@ -1271,10 +1277,17 @@ inline int dense_dual_setup(DensePlan& dp, const DevP& p, bool tiled_chains, std
         return true;
     };
     double *pf = nullptr, *pa = nullptr, *tf = nullptr, *ta = nullptr, *tmp = nullptr;
-    if (!dalloc(&pf, (size_t)nP * 2 * hplane) || !dalloc(&pa, (size_t)nP * 2 * hplane)) return 0;
-    if (ns == 3 && (!dalloc(&tf, (size_t)nP3 * 2 * hplane) || !dalloc(&ta, (size_t)nP3 * 2 * hplane) || !dalloc(&tmp, 2 * hplane))) return 0;
+    // Hermitian generators: the adjoints are the operators themselves, one set of products serves both sweeps
+    if (!dalloc(&pf, (size_t)nP * 2 * hplane)) return 0;
+    if (d.herm) pa = pf;
+    else if (!dalloc(&pa, (size_t)nP * 2 * hplane)) return 0;
+    if (ns == 3) {
+        if (!dalloc(&tf, (size_t)nP3 * 2 * hplane) || !dalloc(&tmp, 2 * hplane)) return 0;
+        if (d.herm) ta = tf;
+        else if (!dalloc(&ta, (size_t)nP3 * 2 * hplane)) return 0;
+    }
     dim3 grid((d.Np + 31) / 32, (d.Np + 7) / 8);
-    for (int side = 0; side < 2; ++side) {
+    for (int side = 0; side < (d.herm ? 1 : 2); ++side) {
         const double* Hm = side ? d.Ha : d.Hf;
         double* P = side ? pa : pf;
         double* T = side ? ta : tf;
@@ -1301,6 +1314,10 @@ inline int dense_dual_setup(DensePlan& dp, const DevP& p, bool tiled_chains, std
             }
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { err = std::string("operator products failed: ") + cudaGetErrorString(cudaGetLastError()); return GRAPE_B200_ECUDA; }
+    if (tiled_chains) {   // kernel attributes: dense2_multi_setup
+        d.PPf = pf; d.PPa = pa; d.nP = nP; d.PTf = tf; d.PTa = ta; d.nP3 = nP3; d.nstrip = ns;
+        return 0;
+    }
     const size_t smem = smem_of(ns);
     cudaError_t e = ns == 3 ? cudaFuncSetAttribute(dense_chain<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                             : cudaFuncSetAttribute(dense_chain<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

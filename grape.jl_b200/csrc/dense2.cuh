@@ -574,7 +574,8 @@ struct Dense2Plan {
     bool on;
     int grid;
     size_t smemF, smemB;
-    Dense2Plan() : on(false), grid(0), smemF(0), smemB(0) { memset(&d2, 0, sizeof d2); }
+    size_t smemM;   // dense2_chain_multi<BWD, NS>
+    Dense2Plan() : on(false), grid(0), smemF(0), smemB(0), smemM(0) { memset(&d2, 0, sizeof d2); }
 };
 
 template <int LB>
@@ -647,6 +648,8 @@ inline int dense2_setup(Dense2Plan& q, DensePlan& dp, DevP& p, std::vector<void*
     return 0;
 }
 
+inline void dense2_chain_multi_launch(Dense2Plan& q, bool bwd, int ns, void** args, cudaStream_t st);
+
 inline void dense2_run_forward(Dense2Plan& q, DensePlan& dp, const DevP& p, cudaStream_t st, int64_t& launches) {
     DenseDev& d = dp.d;
     const size_t splane = (size_t)d.Np * d.Kp;
@@ -655,7 +658,12 @@ inline void dense2_run_forward(Dense2Plan& q, DensePlan& dp, const DevP& p, cuda
     if (p.gb_kind) cudaMemsetAsync(d.jbpart, 0, (size_t)q.d2.tilesR * d.Kp * sizeof(double), st);
     DevP pp = p;
     void* args[] = {&pp, &d, &q.d2, &dp.kd};
-    cudaLaunchCooperativeKernel((void*)dense2_chain<false>, dim3(q.grid), dim3(D2_THREADS), args, q.smemF, st);
+    if (d.nstrip > 1) {
+        dense_run_preform(dp, p, false, st, launches);
+        dense2_chain_multi_launch(q, false, d.nstrip, args, st);
+    } else {
+        cudaLaunchCooperativeKernel((void*)dense2_chain<false>, dim3(q.grid), dim3(D2_THREADS), args, q.smemF, st);
+    }
     dense_tau<<<p.K, 256, 0, st>>>(p, d, q.d2.tilesR);
     launches += 2;
 }
@@ -678,7 +686,336 @@ inline void dense2_run_backward(Dense2Plan& q, DensePlan& dp, const DevP& p, con
     launches += 2;
     if (dp.kd.on) {
         void* cargs[] = {&pp, &d, &q.d2, &dp.kd};
+        if (d.nstrip > 1) {
+            if (d.preA != d.preF) dense_run_preform(dp, p, true, st, launches);
+            dense2_chain_multi_launch(q, true, d.nstrip, cargs, st);
+        } else {
             cudaLaunchCooperativeKernel((void*)dense2_chain<true>, dim3(q.grid), dim3(D2_THREADS), cargs, q.smemF, st);
+        }
         launches += 1;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Tiled chain with NS = 2 or 3 Taylor terms per grid barrier (see dense_chain<BWD, NS> in dense.cuh):
+//   T_{j+q} = (-+i dt)^q / ((j+1)..(j+q)) H_n^q T_j,  q = 1..NS,
+// one staged chunk of the operand block T_j feeds NS products with the tiles of H_n, H_n^2 [, H_n^3], which are read
+// from the generators pre-formed for all steps of the call (dense_preform; no per-step formation in this kernel).
+// ---------------------------------------------------------------------------
+template <int NS>
+__host__ __device__ constexpr size_t d2m_stage_doubles() { return (size_t)NS * 2 * D2_TM * (D2_KC_F + 4) + 2 * D2_KC_F * D2_BS; }
+
+// stage layout: A_q plane pl at ((q*2+pl)*TM + r)*AS, then B plane pl at ((pl)*KC + kr)*BS
+template <int NS>
+GB_D void d2m_issue(double* __restrict__ stage, const double* __restrict__ A, size_t aplane, int lda,
+                    const double* __restrict__ B, size_t bplane, int ldb, int k0, int nt) {
+    constexpr int KC = D2_KC_F, AS = KC + 4, HS = KC / 2, ASEG = 2 * D2_TM * HS, TS = D2_TN / 2, BSEG = 2 * KC * TS;
+    double* bst = stage + NS * 2 * D2_TM * AS;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        if (q < nt) {
+#pragma unroll
+            for (int e0 = 0; e0 < ASEG; e0 += D2_THREADS) {
+                const int e = e0 + threadIdx.x;
+                const int s = e % HS, r = (e / HS) % D2_TM, pl = e / (HS * D2_TM);
+                if (ASEG % D2_THREADS == 0 || e < ASEG)
+                    cp_async16(stage + ((q * 2 + pl) * D2_TM + r) * AS + 2 * s, A + (size_t)(2 * q + pl) * aplane + (size_t)r * lda + k0 + 2 * s);
+            }
+        }
+    }
+#pragma unroll
+    for (int e0 = 0; e0 < BSEG; e0 += D2_THREADS) {
+        const int e = e0 + threadIdx.x;
+        const int s = e % TS, kr = (e / TS) % KC, pl = e / (TS * KC);
+        if (BSEG % D2_THREADS == 0 || e < BSEG)
+            cp_async16(bst + (pl * KC + kr) * D2_BS + 2 * s, B + pl * bplane + (size_t)(k0 + kr) * ldb + 2 * s);
+    }
+}
+
+// out[q] = sum_k A_q[r][k] B[k][c], q < nt; warp = 16x16 block over one quarter of every staged chunk (as
+// d2_tile_gemm_k4); result in the per-thread mapping row wr*8+lr, columns wc*8+2lc+{0,1}.
+template <int NS>
+GB_D void d2m_tile_gemm(double* __restrict__ sm, const double* __restrict__ A, size_t aplane, int lda,
+                        const double* __restrict__ B, size_t bplane, int ldb, int Nk, int nt, D2Acc (&out)[NS]) {
+    constexpr int KC = D2_KC_F, AS = KC + 4, RS = 24;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int kq = w & 3, rh = w >> 2;
+    constexpr size_t SD = d2m_stage_doubles<NS>();
+    D2Acc acc[NS][2][2];
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[q][i][j].re[0] = acc[q][i][j].re[1] = acc[q][i][j].im[0] = acc[q][i][j].im[1] = 0.0;
+#pragma unroll
+    for (int s = 0; s < D2_ST - 1; ++s) {
+        if (s < Nk) d2m_issue<NS>(sm + s * SD, A, aplane, lda, B, bplane, ldb, s * KC, nt);
+        cp_async_commit();
+    }
+    for (int c = 0; c < Nk; ++c) {
+        cp_async_wait<D2_ST - 2>();
+        __syncthreads();
+        const int nx = c + D2_ST - 1;
+        if (nx < Nk) d2m_issue<NS>(sm + (nx % D2_ST) * SD, A, aplane, lda, B, bplane, ldb, nx * KC, nt);
+        cp_async_commit();
+        const double* st = sm + (c % D2_ST) * SD;
+        const double* bst = st + NS * 2 * D2_TM * AS;
+#pragma unroll
+        for (int kk = 0; kk < KC / 16; ++kk) {
+            const int ko = kq * (KC / 4) + kk * 4 + lc;
+            double bre[2], bim[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                bre[j] = bst[(0 * KC + ko) * D2_BS + j * 8 + lr];
+                bim[j] = bst[(1 * KC + ko) * D2_BS + j * 8 + lr];
+            }
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                if (q < nt) {
+                    double are[2], aim[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        are[i] = st[((q * 2 + 0) * D2_TM + rh * 16 + i * 8 + lr) * AS + ko];
+                        aim[i] = st[((q * 2 + 1) * D2_TM + rh * 16 + i * 8 + lr) * AS + ko];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            dmma884(acc[q][i][j].re, are[i], bre[j]);
+                            dmma884(acc[q][i][j].im, are[i], bim[j]);
+                        }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const double nai = -aim[i];
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            dmma884(acc[q][i][j].re, nai, bim[j]);
+                            dmma884(acc[q][i][j].im, aim[i], bre[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();   // every warp is done with the stage buffers: reuse them for the partial sums
+    // red[q][kq][plane][row 0..31][RS]
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        if (q < nt) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int row = rh * 16 + i * 8 + lr, col = j * 8 + 2 * lc;
+                    *reinterpret_cast<double2*>(&sm[(((q * 4 + kq) * 2 + 0) * D2_TM + row) * RS + col]) = make_double2(acc[q][i][j].re[0], acc[q][i][j].re[1]);
+                    *reinterpret_cast<double2*>(&sm[(((q * 4 + kq) * 2 + 1) * D2_TM + row) * RS + col]) = make_double2(acc[q][i][j].im[0], acc[q][i][j].im[1]);
+                }
+        }
+    }
+    __syncthreads();
+    {
+        const int wr = w >> 1, wc = w & 1;
+        const int row = wr * 8 + lr, col = wc * 8 + 2 * lc;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            double2 r = make_double2(0.0, 0.0), im = make_double2(0.0, 0.0);
+            if (q < nt) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const double2 a = *reinterpret_cast<const double2*>(&sm[(((q * 4 + t) * 2 + 0) * D2_TM + row) * RS + col]);
+                    const double2 b = *reinterpret_cast<const double2*>(&sm[(((q * 4 + t) * 2 + 1) * D2_TM + row) * RS + col]);
+                    r.x += a.x; r.y += a.y; im.x += b.x; im.y += b.y;
+                }
+            }
+            out[q].re[0] = r.x; out[q].re[1] = r.y; out[q].im[0] = im.x; out[q].im[1] = im.y;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool BWD, int NS>
+__global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain_multi(DevP p, DenseDev d, Dense2Dev d2, KryDev kd) {
+    if (BWD && !(*kd.ok)) return;   // uniform over the grid
+    cgx::grid_group grid = cgx::this_grid();
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ double s_gb[4][D2_TN];
+    const int Np = d.Np, Kp = d.Kp, NT = p.NT;
+    const size_t splane = (size_t)Np * Kp, hplane = (size_t)Np * Np;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lr = lane >> 2, lc = lane & 3, wr = w >> 1, wc = w & 1;
+    const int NkF = Np / D2_KC_F;
+    const bool gb = BWD ? (p.gb_kind != 0 && p.lambda_b != 0.0) : (p.gb_kind != 0);
+    double* cur = BWD ? kd.kcur : d.cur;
+    double* nxt = BWD ? kd.kcur2 : d2.cur2;
+    double* const cur_first = cur;
+    const double* pre = BWD ? d.preA : d.preF;
+    double* terms = BWD ? kd.BT : kd.FT;
+
+    auto gb_point = [&](double wgt) {   // J_b contribution of the state in `cur`: Re <psi|D|psi> per trajectory
+        for (int t = blockIdx.x; t < d2.ntiles; t += gridDim.x) {
+            const int rt = t / d2.tilesC, ct = t % d2.tilesC;
+            const int r0 = rt * D2_TM, c0 = ct * D2_TN;
+            D2Acc acc[1];
+            d2_tile_gemm_k4(dsm, d.Dm + (size_t)r0 * Np, hplane, Np, cur + c0, splane, Kp, NkF, acc[0]);
+            const int row = r0 + wr * 8 + lr;
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const size_t off = (size_t)row * Kp + c0 + wc * 8 + 2 * lc + e;
+                v[e] = cur[off] * acc[0].re[e] + cur[splane + off] * acc[0].im[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                v[e] += __shfl_xor_sync(0xffffffffu, v[e], 4);
+                v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+                v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+            }
+            if (lr == 0) { s_gb[wr][wc * 8 + 2 * lc] = v[0]; s_gb[wr][wc * 8 + 2 * lc + 1] = v[1]; }
+            __syncthreads();
+            if (threadIdx.x < D2_TN) {
+                const double sacc = s_gb[0][threadIdx.x] + s_gb[1][threadIdx.x] + s_gb[2][threadIdx.x] + s_gb[3][threadIdx.x];
+                d.jbpart[(size_t)rt * Kp + c0 + threadIdx.x] += wgt * sacc;
+            }
+            __syncthreads();
+        }
+    };
+
+    if (BWD) {   // slot 0 of the last step = chi(T)
+        double* s0 = terms + (size_t)(NT - 1) * kd.MT * 2 * splane;
+        for (size_t e = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e < 2 * splane; e += (size_t)gridDim.x * D2_THREADS)
+            s0[e] = cur[e];
+        grid.sync();
+    }
+    for (int it = 0; it < NT; ++it) {
+        const int n = BWD ? NT - 1 - it : it;
+        const double dt = p.tlist[n + 1] - p.tlist[n];
+        const double* Hq = pre + (size_t)n * (2 * NS) * hplane;   // planes {Re H, Im H, Re H^2, Im H^2, ..}
+        if (!BWD && gb) gb_point(n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]));
+        int m, s;
+        dense_plan(p, d, n, dt, m, s);
+        if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
+            p.flags->taylor_fail = 1;
+        const bool kry = kd.on && s == 0 && m <= kd.MT;
+        double* slots = kry ? terms + (size_t)n * kd.MT * 2 * splane : nullptr;
+        const bool multi = kry && m >= 2;
+        const int nsub = 1 << s;
+        const double dts = dt / nsub;
+        for (int sub = 0; sub < nsub; ++sub) {
+            const bool last = sub == nsub - 1;
+            // stage = NS terms (multi) or one term; jt = index of the first term of the stage (1-based)
+            for (int j = 1; j <= m; j += (multi ? NS : 1)) {
+                const int nt = multi ? min(NS, m - j + 1) : 1;
+                const double* src = j == 1 ? cur : (kry ? slots + (size_t)(j - 1) * 2 * splane : ((j - 1) & 1 ? d.T1 : d.T0));
+                const bool fin = (j + nt - 1 == m) && last;
+                double xq[NS];
+                {
+                    double x = 1.0;
+#pragma unroll
+                    for (int q = 0; q < NS; ++q) { x *= dts / (j + q); xq[q] = x; }
+                }
+                for (int t = blockIdx.x; t < d2.ntiles; t += gridDim.x) {
+                    const int r0 = (t / d2.tilesC) * D2_TM, c0 = (t % d2.tilesC) * D2_TN;
+                    const int row = r0 + wr * 8 + lr;
+                    const int kc = c0 + wc * 8 + 2 * lc;
+                    const size_t off = (size_t)row * Kp + kc;
+                    const double* base = j == 1 ? cur : nxt;
+                    const double2 b_r = *reinterpret_cast<const double2*>(&base[off]);
+                    const double2 b_i = *reinterpret_cast<const double2*>(&base[splane + off]);
+                    D2Acc acc[NS];
+                    d2m_tile_gemm<NS>(dsm, Hq + (size_t)r0 * Np, hplane, Np, src + c0, splane, Kp, NkF, nt, acc);
+                    double vr[2] = {b_r.x, b_r.y}, vi[2] = {b_i.x, b_i.y};
+#pragma unroll
+                    for (int q = 0; q < NS; ++q) {
+                        if (q < nt) {
+                            // f_q res: q = 0: (-+i) x res; q = 1: -x res; q = 2: (+-i) x res   (forward: -i, backward: +i)
+                            double tr[2], ti[2];
+                            const double x = xq[q];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                if (q == 0) { tr[e] = BWD ? -x * acc[q].im[e] : x * acc[q].im[e]; ti[e] = BWD ? x * acc[q].re[e] : -x * acc[q].re[e]; }
+                                else if (q == 1) { tr[e] = -x * acc[q].re[e]; ti[e] = -x * acc[q].im[e]; }
+                                else { tr[e] = BWD ? x * acc[q].im[e] : -x * acc[q].im[e]; ti[e] = BWD ? -x * acc[q].re[e] : x * acc[q].re[e]; }
+                                vr[e] += tr[e];
+                                vi[e] += ti[e];
+                            }
+                            if (j + q < m) {
+                                double* dst = kry ? slots + (size_t)(j + q) * 2 * splane : (((j + q) & 1) ? d.T1 : d.T0);
+                                *reinterpret_cast<double2*>(&dst[off]) = make_double2(tr[0], tr[1]);
+                                *reinterpret_cast<double2*>(&dst[splane + off]) = make_double2(ti[0], ti[1]);
+                            }
+                        }
+                    }
+                    if (BWD && fin && gb && n > 0) {
+                        // chi += lambda_b * 0.5 (t_{n+1} - t_{n-1}) / rho * xi(Psi(t_{n-1})), xi = -D Psi  (optimize.jl:897-908)
+                        const double f = p.lambda_b * 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]);
+                        const double* st = d.store + (size_t)n * 2 * splane;
+                        D2Acc a1[1];
+                        d2_tile_gemm_k4(dsm, d.Dm + (size_t)r0 * Np, hplane, Np, st + c0, splane, Kp, NkF, a1[0]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = kc + e;
+                            if (k < p.K) {
+                                const double fk = f / p.rho[k];
+                                vr[e] -= fk * a1[0].re[e];
+                                vi[e] -= fk * a1[0].im[e];
+                            }
+                        }
+                    }
+                    *reinterpret_cast<double2*>(&nxt[off]) = make_double2(vr[0], vr[1]);
+                    *reinterpret_cast<double2*>(&nxt[splane + off]) = make_double2(vi[0], vi[1]);
+                    if (fin) {
+                        if (!BWD) {
+                            double* st = d.store + (size_t)(n + 1) * 2 * splane;
+                            __stcs(reinterpret_cast<double2*>(&st[off]), make_double2(vr[0], vr[1]));
+                            __stcs(reinterpret_cast<double2*>(&st[splane + off]), make_double2(vi[0], vi[1]));
+                        } else if (n > 0) {   // slot 0 of the next (earlier) step = chi(t_{n-1})
+                            double* s0 = terms + (size_t)(n - 1) * kd.MT * 2 * splane;
+                            *reinterpret_cast<double2*>(&s0[off]) = make_double2(vr[0], vr[1]);
+                            *reinterpret_cast<double2*>(&s0[splane + off]) = make_double2(vi[0], vi[1]);
+                        }
+                    }
+                }
+                grid.sync();
+            }
+            double* tmp = cur; cur = nxt; nxt = tmp;
+        }
+    }
+    if (!BWD) {
+        if (gb) gb_point(0.5 * (p.tlist[NT] - p.tlist[NT - 1]));
+        if (cur != cur_first) {   // final state must be in d.cur (read by dense_tau / dense_boundary / read-backs)
+            for (size_t e = (size_t)blockIdx.x * D2_THREADS + threadIdx.x; e < 2 * splane; e += (size_t)gridDim.x * D2_THREADS)
+                cur_first[e] = cur[e];
+        }
+    }
+}
+
+inline void dense2_chain_multi_launch(Dense2Plan& q, bool bwd, int ns, void** args, cudaStream_t st) {
+    void* fn = bwd ? (ns == 3 ? (void*)dense2_chain_multi<true, 3> : (void*)dense2_chain_multi<true, 2>)
+                   : (ns == 3 ? (void*)dense2_chain_multi<false, 3> : (void*)dense2_chain_multi<false, 2>);
+    cudaLaunchCooperativeKernel(fn, dim3(q.grid), dim3(D2_THREADS), args, q.smemM, st);
+}
+
+// after dense_dual_setup (which decided DenseDev::nstrip and allocated the pre-formed generators): kernel attributes
+// of the tiled multi-term chain; falls back to one term per barrier if the stages do not fit
+inline int dense2_multi_setup(Dense2Plan& q, DensePlan& dp, std::string& err) {
+    DenseDev& d = dp.d;
+    if (!q.on || d.nstrip < 2) return 0;
+    const size_t smem = sizeof(double) * D2_ST * (d.nstrip == 3 ? d2m_stage_doubles<3>() : d2m_stage_doubles<2>());
+    cudaError_t e = cudaErrorInvalidValue;
+    if (smem <= 227 * 1024) {
+        if (d.nstrip == 3) {
+            e = cudaFuncSetAttribute(dense2_chain_multi<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(dense2_chain_multi<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        } else {
+            e = cudaFuncSetAttribute(dense2_chain_multi<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(dense2_chain_multi<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); d.nstrip = 1; return 0; }
+    q.smemM = smem;
+    (void)err;
+    return 0;
 }

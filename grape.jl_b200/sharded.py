@@ -8,6 +8,8 @@ the sum over k):
   1. all-reduce(sum) of the 4 partial sums (sum w tau, sum w|tau|^2, sum J_b)
      after the forward sweep;
   2. all-reduce(sum) of the partial gradient [L*NT] after the backward sweep.
+For J_T_re / J_T_ss chi_k does not depend on the other trajectories, so (1) is only
+needed for the value of J and travels with (2) in one coalesced NCCL call.
 The host-side optimizer step is unchanged and identical on every rank."""
 from __future__ import annotations
 
@@ -143,15 +145,47 @@ class DevicePipeline:
         self.sums_t = torch.as_tensor(_DevArray(engine.device_ptr(1), 4), device=dev)
         self.gTb_t = torch.as_tensor(_DevArray(engine.device_ptr(0), LNT), device=dev)
         self.G_t = torch.as_tensor(_DevArray(engine.device_ptr(3), LNT), device=dev)
+        # J_T_sm: chi_k is proportional to sum_j tau_j (reference docs/src/tutorial.md:399-405), so the backward sweep
+        # needs the global sums. J_T_re / J_T_ss: chi_k only depends on tau_k, the sums are needed for J alone, and
+        # both exchanges travel in ONE coalesced NCCL call after the backward sweep.
+        self.coupled = int(getattr(engine.problem, "functional", 0)) == 0
+        self.coalesce = False
+        if dist is not None and not self.coupled:
+            self.coalesce = self._probe_coalescing(torch, dev)
+
+    def _probe_coalescing(self, torch, dev):
+        """one coalesced all-reduce of two scratch tensors on every rank: usable iff it returns the right sums"""
+        d = self.dist
+        try:
+            a = torch.ones(4, dtype=torch.float64, device=dev)
+            b = torch.full((8,), 2.0, dtype=torch.float64, device=dev)
+            with d._coalescing_manager(group=self.group):
+                d.all_reduce(a, op=d.ReduceOp.SUM, group=self.group)
+                d.all_reduce(b, op=d.ReduceOp.SUM, group=self.group)
+            w = float(d.get_world_size(self.group))
+            ok = bool(torch.all(a == w).item() and torch.all(b == 2.0 * w).item())
+        except Exception:
+            ok = False
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        d.all_reduce(flag, op=d.ReduceOp.MIN, group=self.group)      # all ranks must take the same path
+        return bool(flag.item() == 1.0)
 
     def step(self, d_eps):
-        e = self.engine
+        e, d = self.engine, self.dist
         e.enqueue_forward(d_eps.data_ptr())
-        if self.dist is not None:
-            self.dist.all_reduce(self.sums_t, op=self.dist.ReduceOp.SUM, group=self.group)
+        if d is not None and self.coupled:
+            d.all_reduce(self.sums_t, op=d.ReduceOp.SUM, group=self.group)
         e.enqueue_backward()
-        if self.dist is not None:
-            self.dist.all_reduce(self.gTb_t, op=self.dist.ReduceOp.SUM, group=self.group)
+        if d is not None:
+            if self.coupled:
+                d.all_reduce(self.gTb_t, op=d.ReduceOp.SUM, group=self.group)
+            elif self.coalesce:
+                with d._coalescing_manager(group=self.group):
+                    d.all_reduce(self.sums_t, op=d.ReduceOp.SUM, group=self.group)
+                    d.all_reduce(self.gTb_t, op=d.ReduceOp.SUM, group=self.group)
+            else:
+                d.all_reduce(self.sums_t, op=d.ReduceOp.SUM, group=self.group)
+                d.all_reduce(self.gTb_t, op=d.ReduceOp.SUM, group=self.group)
             e.enqueue_combine()
 
     def finish(self):

@@ -179,7 +179,9 @@ int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, d
  * the caller's collective library on the handle's stream:
  *   enqueue_forward(d_pulsevals)  -> local sums at device_ptr(1)      [all-reduce in place]
  *   enqueue_backward()            -> local grad_J_Tb at device_ptr(0) [all-reduce in place]
- *   enqueue_combine()             -> G = grad_J_Tb + lambda_a*grad_J_a at device_ptr(3)
+ *   enqueue_combine()             -> G = grad_J_Tb + lambda_a*grad_J_a at device_ptr(3), J_parts from the current sums
+ * For J_T_re / J_T_ss (chi_k does not depend on the other trajectories) the first all-reduce may be deferred and
+ * fused with the second: enqueue_forward, enqueue_backward, ONE all-reduce of {sums[4], grad_J_Tb}, enqueue_combine.
  *   finish()                      -> synchronise, report chi-norm / Taylor errors
  * With one shard, enqueue_forward + enqueue_backward + finish is a complete
  * evaluate_gradient! (G at device_ptr(3)). */

@@ -207,27 +207,33 @@ def test_large_n_few_trajectories_uses_tiled_kernels(lib_built):
         e.close()
 
 
+@pytest.mark.parametrize("dense2", [0, 1])
 @pytest.mark.parametrize("N,K,NT,L", [(450, 24, 3, 2), (450, 16, 4, 2), (100, 16, 6, 3), (130, 9, 5, 1), (64, 40, 5, 2)])
-def test_two_terms_per_barrier_matches_single_term_chain(lib_built, N, K, NT, L):
-    """strip chains with strips of H_n^2 (and H_n^3): two / three Taylor terms per grid barrier (csrc/dense.cuh
-    dense_chain<BWD, NS>; one or several 8-column groups per CTA, Taylor orders of every residue mod NS, 1..3 controls)
-    against the one-term-per-barrier chain: same truncated series, so J and every gradient element agree to 1e-12"""
+def test_several_terms_per_barrier_match_single_term_chain(lib_built, N, K, NT, L, dense2):
+    """chains with operand tiles of H_n^2 (and H_n^3): two / three Taylor terms per grid barrier (strip kernels
+    csrc/dense.cuh dense_chain<BWD, NS> -- one or several 8-column groups per CTA -- and tiled kernels csrc/dense2.cuh
+    dense2_chain_multi<BWD, NS>; Taylor orders of every residue mod NS, 1..3 controls, Hermitian and non-Hermitian
+    generators) against the one-term-per-barrier chain: same truncated series, so J and every gradient element agree
+    to 1e-12"""
+    if dense2 and ((K + 7) // 8 * 8) % 16 != 0:
+        pytest.skip("trajectory block is not a multiple of the 16-column tile: the strip kernels serve this shape")
     if L == 2:
         p, eps = configs.c4_dense450(N=N, K=K, NT=NT)
     else:
         p, eps = configs.random_problem(K=K, N=N, L=L, NT=NT, G=1, seed=500 + N, hermitian=False, shaped=True)
         p.tlist = p.tlist * (0.5 / np.sqrt(N))
     res = []
-    # three / two Taylor terms per barrier with the generators of all steps pre-formed once per call (strips of H_n,
-    # H_n^2 [, H_n^3] prefetched by cp.async; the non-Hermitian cases keep a second set for the adjoints), two terms with
-    # the chain forming its strips itself, and the single-term chain
-    for terms, pre in ((3, 1), (2, 1), (2, 0), (1, 0)):
-        with _Env(GRAPE_B200_DENSE2=0, GRAPE_B200_DENSE_TERMS=terms, GRAPE_B200_DENSE_PREFORM=pre):
+    # three / two terms per barrier with the generators of all steps pre-formed once per call (tiles of H_n, H_n^2
+    # [, H_n^3] fetched by cp.async; the non-Hermitian cases keep a second set for the adjoints), two terms with the
+    # strip chain forming its strips itself (the tiled chain has no such mode: one term), and the single-term chain
+    modes = ((3, 1, 2), (2, 1, 2), (2, 0, 1 if dense2 else 2), (1, 0, 1))
+    for terms, pre, form in modes:
+        with _Env(GRAPE_B200_DENSE2=dense2, GRAPE_B200_DENSE_TERMS=terms, GRAPE_B200_DENSE_PREFORM=pre):
             e = engine(p)
         G = np.zeros_like(eps)
         for _ in range(2):                       # twice: the prefetch state must not leak between calls
             J = e.evaluate_gradient(G, eps)
-        assert e.gradient_form() == (2 if terms > 1 else 1)
+        assert e.gradient_form() == form, (terms, pre, e.gradient_form())
         res.append((J, G.copy(), e.final_states(), e.stored_states(K - 1)))
         e.close()
     scale = np.max(np.abs(res[3][1]))
@@ -236,7 +242,8 @@ def test_two_terms_per_barrier_matches_single_term_chain(lib_built, N, K, NT, L)
         assert np.max(np.abs(r[1] - res[3][1])) <= 1e-12 * scale
         assert np.max(np.abs(r[2] - res[3][2])) <= 1e-13
         assert np.max(np.abs(r[3] - res[3][3])) <= 1e-13
-    assert np.array_equal(res[1][1], res[2][1])   # same arithmetic, only the operand source differs
+    if not dense2:
+        assert np.array_equal(res[1][1], res[2][1])   # same arithmetic, only the operand source differs
 
 
 def test_two_terms_per_barrier_full_width_oracle(lib_built):

@@ -42,3 +42,40 @@ def test_two_shards_on_one_device_sum_to_full_gradient(lib_built):
         Gs += Gp
     assert np.max(np.abs(Gs - G)) <= 1e-13 * np.max(np.abs(G))
     assert abs(np.sum(Jp) - J) <= 1e-13
+
+
+@pytest.mark.parametrize("fn", [gb.SS, gb.RE])
+def test_single_exchange_for_uncoupled_functionals(lib_built, fn):
+    """J_T_ss / J_T_re: chi_k depends on tau_k only, so the sums may be reduced AFTER the backward sweep, together with
+    the gradient (DevicePipeline.step with more than one rank). Emulated here with two shards on one device: local
+    forward + backward on each, one 'all-reduce' of {sums, grad_J_Tb}, enqueue_combine -> G and J of the full problem."""
+    import torch
+    from grape.jl_b200.engine import GrapeEngine
+    from grape.jl_b200.sharded import DevicePipeline, _DevArray
+    p, eps = configs.c3_ensemble(n_delta=4, n_amp=6, NT=70, functional=fn, ja_kind=1, lambda_a=0.05)
+    e = GrapeEngine(p)
+    G = np.zeros_like(eps)
+    J = e.evaluate_gradient(G, eps)
+    e.close()
+    dev = torch.device("cuda", 0)
+    d_eps = torch.from_numpy(eps).to(dev)
+    shards = [GrapeEngine(p.shard(r, 2)) for r in range(2)]
+    pipes = [DevicePipeline(s) for s in shards]
+    assert all(not q.coupled for q in pipes)
+    for s in shards:
+        s.enqueue_forward(d_eps.data_ptr())
+        s.enqueue_backward()
+        s.finish()
+    sums = sum(q.sums_t.clone() for q in pipes)
+    gTb = sum(q.gTb_t.clone() for q in pipes)
+    for s, q in zip(shards, pipes):
+        q.sums_t.copy_(sums)
+        q.gTb_t.copy_(gTb)
+        torch.cuda.synchronize()
+        s.enqueue_combine()
+        s.finish()
+        Jp = torch.as_tensor(_DevArray(s.device_ptr(4), 3), device=dev).cpu().numpy()
+        assert np.max(np.abs(q.gradient().cpu().numpy() - G)) <= 1e-13 * np.max(np.abs(G))
+        assert abs(float(np.sum(Jp)) - J) <= 1e-13
+    for s in shards:
+        s.close()

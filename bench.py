@@ -360,7 +360,7 @@ def main():
                 peak_source="FP64 DMMA peak measured on this GPU in this run (csrc/peaks.cu); MEASURED_PEAKS.json "
                             "carries no FP64 figure",
                 kernel_ms=k_ms, flops_per_unit_kernel=share, flops_per_unit_step=f_step, taylor_terms=terms,
-                gradient_form={0: "block_recursion", 1: "krylov", 2: "krylov, two Taylor terms per grid barrier"}.get(form, str(form)),
+                gradient_form={0: "block_recursion", 1: "krylov", 2: "krylov, 2-3 Taylor terms per grid barrier"}.get(form, str(form)),
                 flops_per_unit_reference_count=8.0 * p.N * p.N * terms * (2 + 2 * p.L),
                 step_tflops=f_step * units_per_step / (ms_per_step * 1e-3) / 1e12,
                 step_frac=f_step * units_per_step / (ms_per_step * 1e-3) / 1e12 / fp["dmma_tflops"],

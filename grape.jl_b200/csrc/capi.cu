@@ -457,7 +457,7 @@ void run_forward(H* h, bool need_storage = true) {
             else dense_run_forward(h->dense, h->p, h->stream, h->launches);
             break;
     }
-    reduce_tau<<<1, 256, 0, h->stream>>>(h->p);
+    reduce_tau<<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p);   // single block, fixed order; wider for large ensembles
     h->launches++;
 }
 void run_backward(H* h, const cplx* chi_host) {

@@ -32,7 +32,7 @@ GB_D void block_sum(double (&v)[NV], double* s_buf /* [32*NV] */) {
 
 // sums[0..1] = sum_k w_k tau_k ; sums[2] = sum_k w_k |tau_k|^2 ; sums[3] = sum_k J_b_trajectory[k]
 // single block, strided fixed-order accumulation (optimize.jl:752-753, 764-766)
-__global__ void __launch_bounds__(256) reduce_tau(DevP p) {
+__global__ void __launch_bounds__(1024) reduce_tau(DevP p) {
     __shared__ double s_buf[32 * 4];
     double v[4] = {0.0, 0.0, 0.0, 0.0};
     for (int k = threadIdx.x; k < p.K; k += blockDim.x) {

@@ -16,7 +16,8 @@ dense configs[3]/[4] can be selected with --workload c1|c2|c4|c5.
 Multi-GPU (torchrun, one rank per GPU): the ensemble is sharded over ranks
 (weak scaling: every rank holds 4096 trajectories, the ensemble grows with N);
 per gradient there are two all-reduces over NCCL (4 partial sums after the
-forward sweep, the L*NT gradient after the backward sweep).
+forward sweep, the L*NT gradient after the backward sweep); for J_T_ss / J_T_re
+(the default workload) they travel in one coalesced call after the backward sweep.
 
 Prints ONE JSON line (rank 0)."""
 from __future__ import annotations

@@ -169,35 +169,42 @@ __global__ void __launch_bounds__(64) small_segchain_fwd(DevP p, SegArgs a) {
     if (k >= K) return;
     const int g = p.gen[k];
     const cplx* Pg = a.Pseg + g;
-    cplx psi[N], Pn[NN];
+    cplx psi[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         psi[i] = p.psi0[(size_t)i * K + k];
         st_cs(&p.psi[(size_t)i * K + k], psi[i]);
     }
+    // The segment propagators do not depend on the state: the loads of CH segments are issued together (one L2
+    // round trip per CH steps of the chain instead of one per step), then applied one after the other.
+    constexpr int CH = N <= 3 ? 4 : 2;
+    for (int seg0 = 0; seg0 < a.NSEG; seg0 += CH) {
+        cplx Pc[CH][NN];
 #pragma unroll
-    for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[(size_t)c * G]);
-    for (int seg = 0; seg < a.NSEG; ++seg) {
-        cplx Pc[NN];
+        for (int u = 0; u < CH; ++u)
+            if (seg0 + u < a.NSEG) {
 #pragma unroll
-        for (int c = 0; c < NN; ++c) Pc[c] = Pn[c];
-        if (seg + 1 < a.NSEG) {
+                for (int c = 0; c < NN; ++c) Pc[u][c] = __ldg(&Pg[((size_t)(seg0 + u) * NN + c) * G]);
+            }
 #pragma unroll
-            for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[((size_t)(seg + 1) * NN + c) * G]);
-        }
-        cplx nw[N];
+        for (int u = 0; u < CH; ++u) {
+            const int seg = seg0 + u;
+            if (seg < a.NSEG) {
+                cplx nw[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            cplx acc = mk(0.0, 0.0);
+                for (int i = 0; i < N; ++i) {
+                    cplx acc = mk(0.0, 0.0);
 #pragma unroll
-            for (int j = 0; j < N; ++j) cfma(acc, Pc[i * N + j], psi[j]);
-            nw[i] = acc;
-        }
-        const int nb = min(NT, (seg + 1) * a.S);
+                    for (int j = 0; j < N; ++j) cfma(acc, Pc[u][i * N + j], psi[j]);
+                    nw[i] = acc;
+                }
+                const int nb = min(NT, (seg + 1) * a.S);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            psi[i] = nw[i];
-            st_cs(&p.psi[((size_t)nb * N + i) * K + k], psi[i]);
+                for (int i = 0; i < N; ++i) {
+                    psi[i] = nw[i];
+                    st_cs(&p.psi[((size_t)nb * N + i) * K + k], psi[i]);
+                }
+            }
         }
     }
     cplx acc = mk(0.0, 0.0);
@@ -218,9 +225,6 @@ __global__ void __launch_bounds__(64) small_segchain_bwd(DevP p, SegArgs a, cons
     if (k >= K) return;
     const int g = p.gen[k];
     const cplx* Pg = a.Pseg + g;
-    cplx Pn[NN];
-#pragma unroll
-    for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[((size_t)(a.NSEG - 1) * NN + c) * G]);
     cplx x[N];
     if (chi_host) {
 #pragma unroll
@@ -250,27 +254,37 @@ __global__ void __launch_bounds__(64) small_segchain_bwd(DevP p, SegArgs a, cons
         x[i] = cscale(x[i], ir);
         p.chiT[(size_t)k * N + i] = x[i];
     }
-    for (int seg = a.NSEG - 1; seg >= 0; --seg) {
+    // chi at the END of segment `seg` is stored, then chi <- P_seg^dagger chi; P of segment 0 is never needed.
+    // As in the forward chain the propagators of CH segments are loaded together.
+    constexpr int CH = N <= 3 ? 4 : 2;
+    for (int seg0 = a.NSEG - 1; seg0 >= 0; seg0 -= CH) {
+        cplx Pc[CH][NN];
 #pragma unroll
-        for (int i = 0; i < N; ++i) a.chiE[((size_t)seg * N + i) * K + k] = x[i];
-        if (seg == 0) break;
-        cplx Pc[NN];
+        for (int u = 0; u < CH; ++u)
+            if (seg0 - u > 0) {
 #pragma unroll
-        for (int c = 0; c < NN; ++c) Pc[c] = Pn[c];
-        if (seg - 1 > 0) {   // P of segment 0 is never needed
+                for (int c = 0; c < NN; ++c) Pc[u][c] = __ldg(&Pg[((size_t)(seg0 - u) * NN + c) * G]);
+            }
 #pragma unroll
-            for (int c = 0; c < NN; ++c) Pn[c] = __ldg(&Pg[((size_t)(seg - 1) * NN + c) * G]);
+        for (int u = 0; u < CH; ++u) {
+            const int seg = seg0 - u;
+            if (seg >= 0) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) a.chiE[((size_t)seg * N + i) * K + k] = x[i];
+                if (seg > 0) {
+                    cplx nw[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) cfmac(acc, Pc[u][j * N + i], x[j]);   // (P^dagger x)_i
+                        nw[i] = acc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) x[i] = nw[i];
+                }
+            }
         }
-        cplx nw[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            cplx acc = mk(0.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < N; ++j) cfmac(acc, Pc[j * N + i], x[j]);   // (P^dagger x)_i
-            nw[i] = acc;
-        }
-#pragma unroll
-        for (int i = 0; i < N; ++i) x[i] = nw[i];
     }
 }
 

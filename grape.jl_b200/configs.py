@@ -194,6 +194,36 @@ def random_problem(K=3, N=3, L=2, NT=12, G=None, seed=0, hermitian=True, uniform
     return p, eps
 
 
+def lindblad_tls(NT=200, T=5.0, gamma=0.05, K=2, **kw):
+    """Open two-level system as Liouville-space trajectories (reference docs/src/background.md:46, 240-242:
+    density matrices are propagated as vectors under a Liouvillian): rho' = -i[H, rho] + gamma (s rho s^+ -
+    {s^+ s, rho}/2), H = -sigma_z/2 + eps(t) sigma_x, row-major vec(rho) of length N = 4.  The propagator of a step
+    is exp(-i G dt) with the NON-HERMITIAN generator G = i L (L the Liouvillian), which is linear in the control:
+    G = (H (x) 1 - 1 (x) H^T) + i D.  Trajectories: rho(0) = |0><0| -> |1><1| and the maximally mixed state -> itself
+    ... K = 2; `J_T_re` with tau_k = <<rho_tgt | rho(T)>> = Tr(rho_tgt rho(T))."""
+    tlist = np.linspace(0.0, T, NT + 1)
+    sz = np.diag([1.0, -1.0]).astype(np.complex128)
+    sx = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+    sm = np.array([[0, 1], [0, 0]], dtype=np.complex128)       # |0><1|: decay 1 -> 0
+    I2 = np.eye(2, dtype=np.complex128)
+
+    def comm(H):                                               # vec_r(H rho - rho H) = (H (x) 1 - 1 (x) H^T) vec_r(rho)
+        return np.kron(H, I2) - np.kron(I2, H.T)
+
+    n_op = sm.conj().T @ sm
+    D = gamma * (np.kron(sm, sm.conj()) - 0.5 * np.kron(n_op, I2) - 0.5 * np.kron(I2, n_op.T))
+    G0 = comm(-0.5 * sz) + 1j * D
+    G1 = comm(sx)
+    rho0 = [np.diag([1.0, 0.0]), 0.5 * np.eye(2)][:K]
+    rhoT = [np.diag([0.0, 1.0]), 0.5 * np.eye(2)][:K]
+    psi0 = np.array([r.reshape(-1) for r in rho0], dtype=np.complex128)
+    tgt = np.array([r.reshape(-1) for r in rhoT], dtype=np.complex128)
+    kw.setdefault("functional", RE)
+    p = GrapeProblem(tlist, G0, G1[None], psi0, tgt, name="lindblad_tls", **kw)
+    eps = discretize_on_midpoints(lambda t: 0.3 * flattop(t, T=T, t_rise=0.3), tlist)
+    return p, eps
+
+
 CONFIGS = {
     "c1": c1_readme,
     "c2": c2_transmon,

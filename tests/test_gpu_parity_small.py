@@ -180,3 +180,14 @@ def test_deterministic(lib_built):
     e.evaluate_gradient(G1, eps)
     e.evaluate_gradient(G2, eps)
     assert np.array_equal(G1, G2)
+
+
+def test_liouville_space_trajectories(lib_built):
+    """vectorised density matrices under a Liouvillian (reference docs/src/background.md:46, 240-242): non-Hermitian
+    generator G = iL, N = 4, J_T_re on Tr(rho_tgt rho(T)); general schedule of the small path and plain chains"""
+    for kw in ({}, dict(path=gb.PATH_SMALL_CHAIN), dict(gradient_method=gb.TAYLOR)):
+        p, eps = configs.lindblad_tls(NT=150, gamma=0.1, **kw)
+        e, ref = check(p, eps)
+        tr = np.array([1, 0, 0, 1.0])
+        assert np.max(np.abs(e.stored_states(0).T @ tr - 1.0)) < 1e-12
+        e.close()

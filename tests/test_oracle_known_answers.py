@@ -176,3 +176,34 @@ def test_no_controls_error():
     with pytest.raises(RuntimeError, match="no controls in trajectories: cannot optimize"):
         optimize([traj], np.linspace(0, 1, 11), J_T=J_T_sm, engine_factory=OracleEngine,
                  rethrow_exceptions=True)
+
+
+def test_liouville_space_trajectories():
+    """vectorised density matrices under a Liouvillian (docs/src/background.md:46, 240-242): the path only sees a
+    non-Hermitian generator and longer state vectors.  Trace preservation, agreement of the propagated vec(rho) with a
+    direct integration of the Lindblad equation in matrix form, gradient against finite differences."""
+    p, eps = configs.lindblad_tls(NT=60, gamma=0.2)
+    op = go.from_problem(p)
+    r = go.evaluate_gradient(op, eps)
+    tr = np.array([1, 0, 0, 1.0])
+    for k in range(p.K):
+        st = r["storage"][k]                                   # [4, NT+1], one column per time point
+        assert np.max(np.abs(st.T @ tr - 1.0)) < 1e-13         # Tr rho(t) = 1 at every time point
+        rho = st[:, -1].reshape(2, 2)
+        assert np.max(np.abs(rho - rho.conj().T)) < 1e-13 and np.min(np.linalg.eigvalsh(rho)) > -1e-13
+    # matrix-form reference: rho <- expm(L dt) rho with L built from H and the jump operator explicitly
+    sz, sx = np.diag([1.0, -1.0]), np.array([[0, 1.0], [1, 0]])
+    sm = np.array([[0, 1.0], [0, 0]])
+    rho = np.diag([1.0, 0.0]).astype(complex)
+    dts = np.diff(p.tlist)
+    for n in range(p.NT):
+        H = -0.5 * sz + eps[n] * sx
+
+        def rhs(x):
+            return -1j * (H @ x - x @ H) + 0.2 * (sm @ x @ sm.T - 0.5 * (sm.T @ sm @ x + x @ sm.T @ sm))
+        Lmat = np.array([rhs(np.eye(4)[i].reshape(2, 2).astype(complex)).reshape(-1) for i in range(4)]).T
+        rho = (expm(Lmat * dts[n]) @ rho.reshape(-1)).reshape(2, 2)
+    assert np.max(np.abs(rho.reshape(-1) - r["storage"][0][:, -1])) < 1e-12
+    fd = go.finite_difference_gradient(op, eps, range(0, len(eps), 7), h=1e-6)
+    assert np.max(np.abs(fd - r["G"][::7])) < 1e-7 * max(1.0, np.max(np.abs(r["G"])))
+    assert r["J"] < 1.0 and np.max(np.abs(r["G"])) > 1e-4      # the control does something

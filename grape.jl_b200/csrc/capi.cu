@@ -502,8 +502,8 @@ void run_gradient(H* h) {
 }
 void run_finalize(H* h, bool grad) {
     if (grad) {
-        const int blocks = (h->LNT + 255) / 256;
-        finalize_grad<<<blocks < 296 ? blocks : 296, 256, 0, h->stream>>>(h->p);
+        const int blocks = (h->LNT + 31) / 32;
+        finalize_grad<<<blocks < 592 ? blocks : 592, 256, 0, h->stream>>>(h->p);
         h->launches++;
     }
     finalize_J<<<1, 256, 0, h->stream>>>(h->p);

@@ -78,20 +78,36 @@ __global__ void __launch_bounds__(256) finalize_J(DevP p) {
 
 // grad_J_Tb[idx] = -2 * sum_kb partial[kb][idx]   (optimize.jl:574-584)
 // grad_J_a[idx]  = 2 eps dt (fluence) ; G = grad_J_Tb + lambda_a grad_J_a  (optimize.jl:1003-1011)
+// A block sums 32 gradient elements: warp w takes the slabs kb = w, w + 8, .. (coalesced over idx, the loads of a
+// warp are independent), the eight partial sums meet in shared memory in fixed order (deterministic run to run).
 __global__ void __launch_bounds__(256) finalize_grad(DevP p) {
+    __shared__ double s_part[8][32];
     const int LNT = p.L * p.NT;
     const int KB = p.KBdev ? *p.KBdev : p.KB;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < LNT; idx += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = blockIdx.x * 32; base < LNT; base += gridDim.x * 32) {
+        const int idx = base + lane;
         double s = 0.0;
-        for (int kb = 0; kb < KB; ++kb) s += p.partial[(size_t)kb * LNT + idx];
-        const double gT = -2.0 * s;
-        double ga = 0.0;
-        if (p.ja_kind == 1) {
-            const int n = idx % p.NT;
-            ga = 2.0 * p.eps[idx] * (p.tlist[n + 1] - p.tlist[n]);
+        if (idx < LNT) {
+#pragma unroll 4
+            for (int kb = w; kb < KB; kb += 8) s += p.partial[(size_t)kb * LNT + idx];
         }
-        p.grad[idx] = p.ja_kind ? fma(p.lambda_a, ga, gT) : gT;
-        p.grad[LNT + idx] = gT;
-        p.grad[2 * LNT + idx] = ga;
+        s_part[w][lane] = s;
+        __syncthreads();
+        if (w == 0 && idx < LNT) {
+            double t = s_part[0][lane];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) t += s_part[q][lane];
+            const double gT = -2.0 * t;
+            double ga = 0.0;
+            if (p.ja_kind == 1) {
+                const int n = idx % p.NT;
+                ga = 2.0 * p.eps[idx] * (p.tlist[n + 1] - p.tlist[n]);
+            }
+            p.grad[idx] = p.ja_kind ? fma(p.lambda_a, ga, gT) : gT;
+            p.grad[LNT + idx] = gT;
+            p.grad[2 * LNT + idx] = ga;
+        }
+        __syncthreads();
     }
 }

@@ -207,3 +207,33 @@ def test_liouville_space_trajectories():
     fd = go.finite_difference_gradient(op, eps, range(0, len(eps), 7), h=1e-6)
     assert np.max(np.abs(fd - r["G"][::7])) < 1e-7 * max(1.0, np.max(np.abs(r["G"])))
     assert r["J"] < 1.0 and np.max(np.abs(r["G"])) > 1e-4      # the control does something
+
+
+@pytest.mark.parametrize("hermitian", [True, False])
+@pytest.mark.parametrize("functional", [gb.SM, gb.RE, gb.SS])
+def test_gradient_against_richardson_extrapolated_differences(functional, hermitian):
+    """The 1e-10 parity bar of north_star is only meaningful if the oracle's gradient itself is right to better than
+    that.  Central differences of the oracle's OWN functional at h, h/2, h/4 with two Richardson steps (error O(h^6))
+    reproduce every sampled gradient element to 1e-11 relative -- with amplitude shapes, weights, J_a, the state
+    running cost and non-Hermitian generators.  The gradient is thereby pinned to the functional, which is pinned by
+    the analytic Rabi value and the reference's own known answers above."""
+    D = np.diag([0.0, 1.0, 0.5])
+    p, eps = configs.random_problem(K=2, N=3, L=2, NT=8, seed=11, functional=functional, shaped=True,
+                                    hermitian=hermitian, gb_kind=gb.GB_QUADFORM, gb_D=D, lambda_b=0.4,
+                                    ja_kind=gb.JA_FLUENCE, lambda_a=0.3, weights=np.array([0.7, 1.3]))
+    op = go.from_problem(p)
+    r = go.evaluate_gradient(op, eps)
+
+    def J(x):
+        return go.evaluate_functional(op, x, want_storage=False)["J"]
+
+    def d1(i, h):
+        e = np.zeros_like(eps)
+        e[i] = h
+        return (J(eps + e) - J(eps - e)) / (2 * h)
+
+    scale = np.max(np.abs(r["G"]))
+    for i in range(0, len(eps), 3):
+        a, b, c = d1(i, 0.04), d1(i, 0.02), d1(i, 0.01)
+        r2 = (16 * (4 * c - b) / 3 - (4 * b - a) / 3) / 15
+        assert abs(r2 - r["G"][i]) <= 1e-11 * scale, (i, r2, r["G"][i])

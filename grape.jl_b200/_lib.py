@@ -63,7 +63,19 @@ SYMBOLS = {
     "grape_b200_launch_count": (C.c_int64, [_P]),
     "grape_b200_gradient_form": (C.c_int, [_P]),
     "grape_b200_small_schedule": (C.c_int, [_P]),
+    "grape_b200_xchg_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "grape_b200_xchg_attach": (C.c_int, [_P, _P]),
+    "grape_b200_xchg_detach": (C.c_int, [_P]),
+    "grape_b200_multi_create": (C.c_int, [C.POINTER(ProblemDesc), C.POINTER(C.c_int32), C.c_int32, C.POINTER(_P)]),
+    "grape_b200_multi_destroy": (None, [_P]),
+    "grape_b200_multi_last_error": (C.c_char_p, [_P]),
+    "grape_b200_multi_eval_f": (C.c_int, [_P, _D, _D, _D]),
+    "grape_b200_multi_eval_fg": (C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
+    "grape_b200_multi_get_final_states": (C.c_int, [_P, _D]),
+    "grape_b200_multi_size": (C.c_int32, [_P]),
+    "grape_b200_multi_shard": (_P, [_P, C.c_int32, C.POINTER(C.c_int32)]),
 }
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 

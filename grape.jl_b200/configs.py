@@ -138,7 +138,8 @@ def _dense(N, K, NT, seeds, name, **kw):
     tlist = 0.25 * np.arange(NT + 1)
     psi0 = np.eye(N, dtype=np.complex128)[:K]
     tgt = np.ascontiguousarray(Q[:, :K].T)
-    p = GrapeProblem(tlist, H0, np.stack([H1, H2]), psi0, tgt, functional=SM, name=name, **kw)
+    kw.setdefault("functional", SM)
+    p = GrapeProblem(tlist, H0, np.stack([H1, H2]), psi0, tgt, name=name, **kw)
     n = np.arange(NT)
     eps = np.concatenate([0.5 * np.sin(np.pi * (l + 2) * (n + 0.5) / NT) for l in range(2)])
     # H_n = H0 + e1 H1 + e2 H2 with |e| <= 0.5: ||H_n dt||_2 <= 0.25 * 2 = 0.5

@@ -8,6 +8,7 @@
 #include "../../include/grape_b200.h"
 #include "common.cuh"
 #include "reduce.cuh"
+#include "xchg.cuh"
 #include "small_n.cuh"
 #include "small_seg.cuh"
 #include "small_sym.cuh"
@@ -70,6 +71,17 @@ struct grape_b200_handle_impl {
     cplx* d_taugrads;     // [K][L][NT] dump buffer of get_tau_grads (allocated on first use)
     bool taugrads_valid;  // d_taugrads holds the tau_grads of the last backward sweep
     SegArgs seg;
+    // peer exchange over NVLink (xchg.cuh): the shards of a trajectory-sharded problem reduce sums / gradient themselves
+    XchgDev xd;
+    bool xchg_on;         // peers attached (grape_b200_xchg_attach / grape_b200_multi_create)
+    bool xchg_mode;       // set by the entry point: true = exchange inside the call (eval_*, enqueue_*), false = local
+                          // partial results (split host API forward / backward / backward_chi)
+    bool xchg_fonly;      // this call is a functional-only evaluation (the sums are always exchanged)
+    void* xchg_buf;       // this handle's exchange buffer: flags | slots | epochs | timeout
+    size_t xchg_bytes;
+    std::vector<void*> xchg_ipc_opened;   // peer buffers opened with cudaIpcOpenMemHandle
+    bool launched_via_graph;              // eval_launch served the call with a graph launch
+    int64_t launch_l0;
 };
 typedef grape_b200_handle_impl H;
 
@@ -433,6 +445,15 @@ void run_fill_interior(H* h) {
         h->interior_done = true;
     }
 }
+bool xchg_live(const H* h) { return h->xchg_on && h->xchg_mode; }
+// first kernel of a sharded evaluation: the epochs of its exchanges (device-side, so that a captured graph replays)
+void run_xchg_begin(H* h, bool grad) {
+    h->xchg_fonly = !grad;
+    if (!xchg_live(h)) return;
+    const int bump0 = (!grad || h->p.functional == GRAPE_B200_JT_SM) ? 1 : 0;
+    xchg_begin<<<1, 1, 0, h->stream>>>(h->xd, bump0, grad ? 1 : 0);
+    h->launches++;
+}
 void run_forward(H* h, bool need_storage = true) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
@@ -459,6 +480,12 @@ void run_forward(H* h, bool need_storage = true) {
     }
     reduce_tau<<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p);   // single block, fixed order; wider for large ensembles
     h->launches++;
+    // sharded over peers: chi of J_T_sm needs the global sum of tau before the backward sweep (optimize.jl:845-855);
+    // a functional-only call needs the global sums for J itself. Otherwise the sums travel with the gradient.
+    if (xchg_live(h) && (h->xchg_fonly || h->p.functional == GRAPE_B200_JT_SM)) {
+        xchg_sums<<<1, 32, 0, h->stream>>>(h->p, h->xd);
+        h->launches++;
+    }
 }
 void run_backward(H* h, const cplx* chi_host) {
     switch (h->path) {
@@ -503,7 +530,11 @@ void run_gradient(H* h) {
 void run_finalize(H* h, bool grad) {
     if (grad) {
         const int blocks = (h->LNT + 31) / 32;
-        finalize_grad<<<blocks < 592 ? blocks : 592, 256, 0, h->stream>>>(h->p);
+        if (xchg_live(h))   // k-reduction fused with the all-reduce over the peers' shards (NVLink stores, xchg.cuh)
+            finalize_grad_xchg<<<blocks < XCHG_MAXB ? blocks : XCHG_MAXB, 256, 0, h->stream>>>(
+                h->p, h->xd, h->p.functional != GRAPE_B200_JT_SM ? 1 : 0);
+        else
+            finalize_grad<<<blocks < 592 ? blocks : 592, 256, 0, h->stream>>>(h->p);
         h->launches++;
     }
     finalize_J<<<1, 256, 0, h->stream>>>(h->p);
@@ -530,6 +561,11 @@ void collect_timings(H* h, int64_t launches_before) {
 int check_flags(H* h) {
     const DevFlags* f = reinterpret_cast<const DevFlags*>(h->h_out + h->off_flags);
     char b[256];
+    if (f->xchg_timeout) {
+        h->err = "peer exchange timed out: a shard of this trajectory-sharded problem did not reach the exchange "
+                 "(every rank must make the same sequence of evaluation calls)";
+        return GRAPE_B200_ENCCL;
+    }
     if (f->chi_bad_k) {
         // message of reference src/optimize.jl:1021-1025
         snprintf(b, sizeof b, "The χ state with index %d has norm %g < %g (chi_min_norm)",
@@ -555,17 +591,24 @@ int upload_pulses(H* h, const double* pulsevals) {
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
     return 0;
 }
-int download_all(H* h) {
+int download_enqueue(H* h) {
     CUDA_TRY(h, cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * h->out_doubles,
                                 cudaMemcpyDeviceToHost, h->stream));
     rec(h, 6);
+    return 0;
+}
+int download_wait(H* h) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
+int download_all(H* h) {
+    if (int rc = download_enqueue(h)) return rc;
+    return download_wait(h);
+}
 
-// Whole-call CUDA graph (small / sub-warp paths, profiling off). Returns 1 if the call was served
-// by a graph launch, 0 if the caller must launch directly, < 0 on error (code negated).
+// Whole-call CUDA graph (small / sub-warp paths, profiling off). Returns 1 if the call was enqueued as a graph
+// launch, 0 if the caller must launch directly, < 0 on error (code negated). No synchronisation.
 int eval_via_graph(H* h, const double* pulsevals, bool grad) {
     if (!h->graphs_ok || h->profiling || h->path == GRAPE_B200_PATH_DENSE) return 0;
     cudaGraphExec_t& ge = grad ? h->graph_fg : h->graph_f;
@@ -580,6 +623,7 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
         const int64_t l0 = h->launches;
         cudaMemcpyAsync(h->d_eps_own, h->h_in, sizeof(double) * h->LNT, cudaMemcpyHostToDevice, h->stream);
         cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream);
+        run_xchg_begin(h, grad);
         run_formU(h);
         run_forward(h, grad);
         if (grad) { run_backward(h, nullptr); run_gradient(h); }
@@ -592,17 +636,53 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
         if (g) cudaGraphDestroy(g);
         if (e != cudaSuccess) { cudaGetLastError(); ge = nullptr; h->graphs_ok = false; return 0; }
     }
+    h->xchg_fonly = !grad;
     if (cudaGraphLaunch(ge, h->stream) != cudaSuccess) { cudaGetLastError(); h->graphs_ok = false; return 0; }
     h->launches += gl;
     // the captured sequence of eval_f leaves the interior of fw_storage unfilled
     if (h->seg_on || h->wseg_on) h->interior_done = grad && !h->seg_herm;
     if (h->path == GRAPE_B200_PATH_SMALL)   // same bookkeeping as run_formU (not executed on a graph replay)
         h->U_valid = !(seg_fused(h) && !h->seg.store_U);
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-        h->err = "CUDA error while executing the evaluation graph";
-        return -GRAPE_B200_ECUDA;
-    }
     return 1;
+}
+void drop_graphs(H* h) {
+    if (h->graph_fg) { cudaGraphExecDestroy(h->graph_fg); h->graph_fg = nullptr; }
+    if (h->graph_f) { cudaGraphExecDestroy(h->graph_f); h->graph_f = nullptr; }
+}
+
+// One complete evaluation (evaluate_functional / evaluate_gradient!, reference src/optimize.jl:696-768, 824-1014),
+// enqueued on the handle's stream without any host synchronisation: H2D of the pulses, the kernel sequence
+// (with the peer exchanges if shards are attached), D2H of the output block.  eval_wait() synchronises.
+int eval_launch(H* h, const double* pulsevals, bool grad) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->xchg_mode = true;
+    h->launch_l0 = h->launches;
+    const int via = eval_via_graph(h, pulsevals, grad);
+    if (via < 0) return -via;
+    h->launched_via_graph = via == 1;
+    if (!via) {
+        rec(h, 0);
+        if (int rc = upload_pulses(h, pulsevals)) return rc;
+        run_xchg_begin(h, grad);
+        run_formU(h); rec(h, 1);
+        run_forward(h, grad); rec(h, 2);   // functional only: the interior of fw_storage is filled lazily (get_stored_states)
+        rec(h, 3);
+        if (grad) { run_backward(h, nullptr); rec(h, 4); run_gradient(h); }
+        else rec(h, 4);
+        run_finalize(h, grad); rec(h, 5);
+        if (int rc = download_enqueue(h)) return rc;
+    }
+    return 0;
+}
+int eval_wait(H* h, bool grad) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        h->err = "CUDA error while executing the evaluation";
+        return GRAPE_B200_ECUDA;
+    }
+    if (!h->launched_via_graph) collect_timings(h, h->launch_l0);
+    h->forward_done = true; h->backward_done = grad; h->taugrads_valid = false;
+    return 0;
 }
 
 }  // namespace
@@ -623,6 +703,8 @@ void grape_b200_destroy(grape_b200_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->graph_fg) cudaGraphExecDestroy(h->graph_fg);
     if (h->graph_f) cudaGraphExecDestroy(h->graph_f);
+    for (void* q : h->xchg_ipc_opened) cudaIpcCloseMemHandle(q);
+    if (h->xchg_buf) cudaFree(h->xchg_buf);
     dense_destroy(h->dense);
     for (void* q : h->dev_allocs) cudaFree(q);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -669,6 +751,8 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
     h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->d_taugrads = nullptr; h->taugrads_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
+    memset(&h->xd, 0, sizeof h->xd); h->xchg_on = false; h->xchg_mode = false; h->xchg_fonly = false;
+    h->xchg_buf = nullptr; h->xchg_bytes = 0; h->launched_via_graph = false; h->launch_l0 = 0;
     h->graph_fg = nullptr; h->graph_f = nullptr; h->graph_fg_launches = h->graph_f_launches = 0;
     h->graphs_ok = !(getenv("GRAPE_B200_NO_GRAPH") && atoi(getenv("GRAPE_B200_NO_GRAPH")) != 0);
     h->device = d->device;
@@ -774,21 +858,19 @@ static void copy_out_common(grape_b200_handle* h, double* J_parts, double* tau) 
 
 int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals, double* J_parts, double* tau) {
     if (!h || !pulsevals) return GRAPE_B200_EINVAL;
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    const int64_t l0 = h->launches;
-    const int via = eval_via_graph(h, pulsevals, false);
-    if (via < 0) return -via;
-    if (!via) {
-        rec(h, 0);
-        if (int rc = upload_pulses(h, pulsevals)) return rc;
-        run_formU(h); rec(h, 1);
-        run_forward(h, false); rec(h, 2);   // interior of fw_storage is filled lazily (get_stored_states)
-        run_finalize(h, false); rec(h, 3); rec(h, 4); rec(h, 5);
-        if (int rc = download_all(h)) return rc;
-        collect_timings(h, l0);
-    }
-    h->forward_done = true; h->backward_done = false; h->taugrads_valid = false;
+    if (int rc = eval_launch(h, pulsevals, false)) return rc;
+    if (int rc = eval_wait(h, false)) return rc;
     if (h->p.functional == GRAPE_B200_JT_HOST) h->h_out[h->off_J] = 0.0 / 0.0;
+    copy_out_common(h, J_parts, tau);
+    return check_flags(h);
+}
+
+static int eval_fg_copy_out(grape_b200_handle* h, double* G, double* J_parts, double* tau, double* grad_J_Tb,
+                            double* grad_J_a) {
+    const int LNT = h->LNT;
+    if (G) memcpy(G, h->h_out, sizeof(double) * LNT);
+    if (grad_J_Tb) memcpy(grad_J_Tb, h->h_out + LNT, sizeof(double) * LNT);
+    if (grad_J_a) memcpy(grad_J_a, h->h_out + 2 * LNT, sizeof(double) * LNT);
     copy_out_common(h, J_parts, tau);
     return check_flags(h);
 }
@@ -800,35 +882,16 @@ int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G,
         h->err = "eval_fg needs a built-in functional; use forward + backward_chi for JT_HOST";
         return GRAPE_B200_EINVAL;
     }
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    const int64_t l0 = h->launches;
-    const int via = eval_via_graph(h, pulsevals, true);
-    if (via < 0) return -via;
-    if (!via) {
-        rec(h, 0);
-        if (int rc = upload_pulses(h, pulsevals)) return rc;
-        run_formU(h); rec(h, 1);
-        run_forward(h); rec(h, 2);
-        rec(h, 3);
-        run_backward(h, nullptr); rec(h, 4);
-        run_gradient(h);
-        run_finalize(h, true); rec(h, 5);
-        if (int rc = download_all(h)) return rc;
-        collect_timings(h, l0);
-    }
-    h->forward_done = true; h->backward_done = true; h->taugrads_valid = false;
-    const int LNT = h->LNT;
-    memcpy(G, h->h_out, sizeof(double) * LNT);
-    if (grad_J_Tb) memcpy(grad_J_Tb, h->h_out + LNT, sizeof(double) * LNT);
-    if (grad_J_a) memcpy(grad_J_a, h->h_out + 2 * LNT, sizeof(double) * LNT);
-    copy_out_common(h, J_parts, tau);
-    return check_flags(h);
+    if (int rc = eval_launch(h, pulsevals, true)) return rc;
+    if (int rc = eval_wait(h, true)) return rc;
+    return eval_fg_copy_out(h, G, J_parts, tau, grad_J_Tb, grad_J_a);
 }
 
 int grape_b200_forward(grape_b200_handle* h, const double* pulsevals, double* tau, double* sums) {
     if (!h || !pulsevals) return GRAPE_B200_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int64_t l0 = h->launches;
+    h->xchg_mode = false;   // split host API: LOCAL partial sums, the caller reduces them over the shards
     rec(h, 0);
     if (int rc = upload_pulses(h, pulsevals)) return rc;
     run_formU(h); rec(h, 1);
@@ -845,6 +908,7 @@ int grape_b200_forward(grape_b200_handle* h, const double* pulsevals, double* ta
 static int backward_common(grape_b200_handle* h, const cplx* chi_host, double* G_partial,
                            double* J_parts, double* J_b_partial, double* grad_J_a) {
     const int64_t l0 = h->launches;
+    h->xchg_mode = false;   // split host API: LOCAL partial gradient
     rec(h, 0); rec(h, 1); rec(h, 2); rec(h, 3);
     run_backward(h, chi_host); rec(h, 4);
     run_gradient(h);
@@ -895,8 +959,10 @@ int grape_b200_enqueue_forward(grape_b200_handle* h, const double* d_pulsevals) 
     if (d_pulsevals != h->d_eps_own)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_eps_own, d_pulsevals, sizeof(double) * h->LNT, cudaMemcpyDeviceToDevice, h->stream));
     h->p.eps = h->d_eps_own;
+    h->xchg_mode = true;    // attached peers: sums / gradient are exchanged inside enqueue_forward / enqueue_backward
     rec(h, 0);
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
+    run_xchg_begin(h, true);
     run_formU(h); rec(h, 1);
     run_forward(h); rec(h, 2); rec(h, 3);
     h->forward_done = true; h->backward_done = false; h->taugrads_valid = false;
@@ -943,7 +1009,9 @@ int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, d
     if (d_pulsevals != h->d_eps_own)
         CUDA_TRY(h, cudaMemcpyAsync(h->d_eps_own, d_pulsevals, sizeof(double) * h->LNT, cudaMemcpyDeviceToDevice, h->stream));
     h->p.eps = h->d_eps_own;
+    h->xchg_mode = true;
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
+    run_xchg_begin(h, true);
     run_formU(h); rec(h, 1);
     run_forward(h); rec(h, 2); rec(h, 3);
     run_backward(h, nullptr); rec(h, 4);
@@ -1107,6 +1175,250 @@ int grape_b200_small_schedule(grape_b200_handle* h) {
         return -GRAPE_B200_ECUDA;
     }
     return nf ? 2 : 3;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Peer exchange over NVLink (xchg.cuh): multi-GPU trajectory sharding behind the ABI
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct XchgLayout { size_t flag_off, slot_off, epoch_off, bytes; int XS; };
+XchgLayout xchg_layout(int world, int LNT) {
+    XchgLayout l;
+    l.XS = (LNT + 4 + 1) & ~1;
+    l.flag_off = 0;
+    size_t o = (size_t)2 * world * XCHG_MAXB * sizeof(unsigned long long);
+    o = (o + 255) & ~(size_t)255;
+    l.slot_off = o;
+    o += (size_t)2 * 2 * world * l.XS * sizeof(double);
+    o = (o + 255) & ~(size_t)255;
+    l.epoch_off = o;
+    l.bytes = o + 256;
+    return l;
+}
+void xchg_release(H* h) {
+    for (void* q : h->xchg_ipc_opened) cudaIpcCloseMemHandle(q);
+    h->xchg_ipc_opened.clear();
+    if (h->xchg_buf) { cudaFree(h->xchg_buf); h->xchg_buf = nullptr; }
+    h->xchg_on = false;
+    memset(&h->xd, 0, sizeof h->xd);
+    drop_graphs(h);
+}
+void xchg_point(H* h, int r, void* base) {
+    const XchgLayout l = xchg_layout(h->xd.world, h->LNT);
+    h->xd.flags[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + l.flag_off);
+    h->xd.slots[r] = reinterpret_cast<double*>(static_cast<char*>(base) + l.slot_off);
+}
+int xchg_init_impl(H* h, int rank, int world) {
+    if (world < 1 || world > XCHG_MAXW || rank < 0 || rank >= world) {
+        h->err = "xchg_init: need 0 <= rank < world <= 16";
+        return GRAPE_B200_EINVAL;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    xchg_release(h);
+    const XchgLayout l = xchg_layout(world, h->LNT);
+    CUDA_TRY(h, cudaMalloc(&h->xchg_buf, l.bytes));
+    CUDA_TRY(h, cudaMemset(h->xchg_buf, 0, l.bytes));
+    h->xchg_bytes = l.bytes;
+    h->xd.rank = rank; h->xd.world = world; h->xd.XS = l.XS;
+    h->xd.epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(h->xchg_buf) + l.epoch_off);
+    h->xd.timeout = &h->p.flags->xchg_timeout;
+    xchg_point(h, rank, h->xchg_buf);
+    return 0;
+}
+}  // namespace
+
+int grape_b200_xchg_init(grape_b200_handle* h, int32_t rank, int32_t world, void* ipc_handle_out) {
+    if (!h) return GRAPE_B200_EINVAL;
+    if (int rc = xchg_init_impl(h, rank, world)) return rc;
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t mh;
+        CUDA_TRY(h, cudaIpcGetMemHandle(&mh, h->xchg_buf));
+        static_assert(sizeof(mh) == GRAPE_B200_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+        memcpy(ipc_handle_out, &mh, sizeof mh);
+    }
+    return 0;
+}
+
+int grape_b200_xchg_attach(grape_b200_handle* h, const void* ipc_handles) {
+    if (!h || !ipc_handles) return GRAPE_B200_EINVAL;
+    if (!h->xchg_buf) { h->err = "xchg_attach before xchg_init"; return GRAPE_B200_ESTATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (int r = 0; r < h->xd.world; ++r) {
+        if (r == h->xd.rank) continue;
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, static_cast<const char*>(ipc_handles) + (size_t)r * GRAPE_B200_IPC_HANDLE_BYTES, sizeof mh);
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            char b[256];
+            snprintf(b, sizeof b, "cudaIpcOpenMemHandle of rank %d's exchange buffer failed: %s (peers need NVLink/P2P access "
+                     "and a shared IPC namespace)", r, cudaGetErrorString(e));
+            h->err = b;
+            cudaGetLastError();
+            return GRAPE_B200_ENCCL;
+        }
+        h->xchg_ipc_opened.push_back(base);
+        xchg_point(h, r, base);
+    }
+    h->xchg_on = h->xd.world > 1;
+    drop_graphs(h);
+    return 0;
+}
+
+int grape_b200_xchg_detach(grape_b200_handle* h) {
+    if (!h) return GRAPE_B200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    xchg_release(h);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One host process driving several GPUs (the `ccall` host of INTEGRATION.md)
+// ------------------------------------------------------------------------------------------------
+struct grape_b200_multi {
+    std::vector<grape_b200_handle*> sh;
+    std::vector<int> k_lo;
+    int K, N, LNT;
+    std::string err;
+};
+namespace { thread_local std::string g_multi_error; }
+
+const char* grape_b200_multi_last_error(const grape_b200_multi* m) { return m ? m->err.c_str() : g_multi_error.c_str(); }
+
+void grape_b200_multi_destroy(grape_b200_multi* m) {
+    if (!m) return;
+    for (auto* h : m->sh) if (h) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); }
+    for (auto* h : m->sh) grape_b200_destroy(h);
+    delete m;
+}
+
+int grape_b200_multi_create(const grape_b200_problem* d, const int32_t* devices, int32_t ndev, grape_b200_multi** out) {
+    if (!out) return GRAPE_B200_EINVAL;
+    *out = nullptr;
+    auto fail = [&](int code, const std::string& msg) { g_multi_error = msg; return code; };
+    if (!d || !devices || ndev < 1 || ndev > XCHG_MAXW) return fail(GRAPE_B200_EINVAL, "multi_create: need 1 <= ndev <= 16 devices");
+    if (d->K < ndev) return fail(GRAPE_B200_EINVAL, "multi_create: fewer trajectories than devices");
+    if (d->K <= 0 || d->N <= 0 || d->L <= 0 || d->NT <= 0 || d->G <= 0 || !d->H0 || !d->Hc || !d->psi0 || !d->tgt)
+        return fail(d->L <= 0 ? GRAPE_B200_ENOCONTROLS : GRAPE_B200_EINVAL,
+                    d->L <= 0 ? "no controls in trajectories: cannot optimize" : "multi_create: invalid descriptor");
+    if (!d->gen_of_traj && d->G != 1 && d->G != d->K)
+        return fail(GRAPE_B200_EINVAL, "gen_of_traj is required unless G == 1 or G == K");
+    grape_b200_multi* m = new grape_b200_multi();
+    m->K = d->K; m->N = d->N; m->LNT = d->L * d->NT;
+    const size_t NN2 = (size_t)2 * d->N * d->N, N2 = (size_t)2 * d->N;
+    for (int i = 0; i < ndev; ++i) {
+        // contiguous block of trajectories; generators no local trajectory uses are dropped
+        const int lo = (int)(((long long)d->K * i) / ndev), hi = (int)(((long long)d->K * (i + 1)) / ndev);
+        const int Kl = hi - lo;
+        std::vector<int> gens, gl(Kl);
+        for (int k = lo; k < hi; ++k) gens.push_back(d->gen_of_traj ? d->gen_of_traj[k] : (d->G == 1 ? 0 : k));
+        std::vector<int> uniq(gens);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        for (int k = 0; k < Kl; ++k) gl[k] = (int)(std::lower_bound(uniq.begin(), uniq.end(), gens[k]) - uniq.begin());
+        const int Gl = (int)uniq.size();
+        std::vector<double> H0((size_t)Gl * NN2), Hc((size_t)Gl * d->L * NN2);
+        for (int g = 0; g < Gl; ++g) {
+            if (uniq[g] < 0 || uniq[g] >= d->G) { grape_b200_multi_destroy(m); return fail(GRAPE_B200_EINVAL, "gen_of_traj entry out of range"); }
+            memcpy(&H0[(size_t)g * NN2], d->H0 + (size_t)uniq[g] * NN2, NN2 * sizeof(double));
+            memcpy(&Hc[(size_t)g * d->L * NN2], d->Hc + (size_t)uniq[g] * d->L * NN2, (size_t)d->L * NN2 * sizeof(double));
+        }
+        grape_b200_problem ld = *d;
+        ld.K = Kl; ld.G = Gl; ld.K_global = d->K_global > 0 ? d->K_global : d->K; ld.device = devices[i];
+        ld.gen_of_traj = gl.data(); ld.H0 = H0.data(); ld.Hc = Hc.data();
+        ld.psi0 = d->psi0 + (size_t)lo * N2; ld.tgt = d->tgt + (size_t)lo * N2;
+        ld.weights = d->weights ? d->weights + lo : nullptr;
+        if (d->gb_kind != GRAPE_B200_GB_NONE && d->gb_D && d->gb_nD == d->K) { ld.gb_D = d->gb_D + (size_t)lo * NN2; ld.gb_nD = Kl; }
+        grape_b200_handle* h = nullptr;
+        const int rc = grape_b200_create(&ld, &h);
+        if (rc) { g_multi_error = g_create_error; grape_b200_multi_destroy(m); return rc; }
+        m->sh.push_back(h);
+        m->k_lo.push_back(lo);
+    }
+    if (ndev > 1) {
+        // every device maps every other device's exchange buffer (NVLink / NVSwitch peer access)
+        for (int i = 0; i < ndev; ++i) {
+            cudaSetDevice(m->sh[i]->device);
+            for (int j = 0; j < ndev; ++j) {
+                if (i == j || m->sh[i]->device == m->sh[j]->device) continue;   // same device: plain device pointers
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, m->sh[i]->device, m->sh[j]->device);
+                if (!can) { grape_b200_multi_destroy(m); return fail(GRAPE_B200_ENCCL, "multi_create: devices have no peer (NVLink/P2P) access to each other"); }
+                cudaError_t e = cudaDeviceEnablePeerAccess(m->sh[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    grape_b200_multi_destroy(m);
+                    return fail(GRAPE_B200_ENCCL, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                }
+                cudaGetLastError();
+            }
+        }
+        for (int i = 0; i < ndev; ++i)
+            if (int rc = xchg_init_impl(m->sh[i], i, ndev)) { g_multi_error = m->sh[i]->err; grape_b200_multi_destroy(m); return rc; }
+        for (int i = 0; i < ndev; ++i) {
+            for (int j = 0; j < ndev; ++j) if (j != i) xchg_point(m->sh[i], j, m->sh[j]->xchg_buf);
+            m->sh[i]->xchg_on = true;
+        }
+    }
+    *out = m;
+    return GRAPE_B200_OK;
+}
+
+int32_t grape_b200_multi_size(const grape_b200_multi* m) { return m ? (int32_t)m->sh.size() : 0; }
+grape_b200_handle* grape_b200_multi_shard(grape_b200_multi* m, int32_t i, int32_t* k_first) {
+    if (!m || i < 0 || i >= (int)m->sh.size()) return nullptr;
+    if (k_first) *k_first = m->k_lo[i];
+    return m->sh[i];
+}
+
+static int multi_eval(grape_b200_multi* m, const double* pulsevals, bool grad, double* G, double* J_parts, double* tau,
+                      double* grad_J_Tb, double* grad_J_a) {
+    if (!m || !pulsevals || (grad && !G)) return GRAPE_B200_EINVAL;
+    // every shard is enqueued before any is waited for: the shards meet in the exchange kernels
+    int rc = 0;
+    size_t launched = 0;
+    for (; launched < m->sh.size(); ++launched) {
+        grape_b200_handle* h = m->sh[launched];
+        if (grad && h->p.functional == GRAPE_B200_JT_HOST) { h->err = "multi_eval_fg needs a built-in functional"; rc = GRAPE_B200_EINVAL; }
+        else rc = eval_launch(h, pulsevals, grad);
+        if (rc) { m->err = h->err; break; }
+    }
+    for (size_t i = 0; i < launched; ++i) {
+        const int rw = eval_wait(m->sh[i], grad);
+        if (rw && !rc) { rc = rw; m->err = m->sh[i]->err; }
+    }
+    if (rc) return rc;
+    for (size_t i = 0; i < m->sh.size(); ++i) {
+        grape_b200_handle* h = m->sh[i];
+        const int rf = check_flags(h);
+        if (rf && !rc) { rc = rf; m->err = h->err; }
+        if (tau) memcpy(tau + (size_t)2 * m->k_lo[i], h->h_out + h->off_tau, 2 * sizeof(double) * h->p.K);
+    }
+    grape_b200_handle* h0 = m->sh[0];
+    if (grad) {
+        memcpy(G, h0->h_out, sizeof(double) * m->LNT);
+        if (grad_J_Tb) memcpy(grad_J_Tb, h0->h_out + m->LNT, sizeof(double) * m->LNT);
+        if (grad_J_a) memcpy(grad_J_a, h0->h_out + 2 * (size_t)m->LNT, sizeof(double) * m->LNT);
+    }
+    if (J_parts) memcpy(J_parts, h0->h_out + h0->off_J, 3 * sizeof(double));
+    return rc;
+}
+int grape_b200_multi_eval_f(grape_b200_multi* m, const double* pulsevals, double* J_parts, double* tau) {
+    return multi_eval(m, pulsevals, false, nullptr, J_parts, tau, nullptr, nullptr);
+}
+int grape_b200_multi_eval_fg(grape_b200_multi* m, const double* pulsevals, double* G, double* J_parts, double* tau,
+                             double* grad_J_Tb, double* grad_J_a) {
+    return multi_eval(m, pulsevals, true, G, J_parts, tau, grad_J_Tb, grad_J_a);
+}
+int grape_b200_multi_get_final_states(grape_b200_multi* m, double* out) {
+    if (!m || !out) return GRAPE_B200_EINVAL;
+    for (size_t i = 0; i < m->sh.size(); ++i) {
+        const int rc = grape_b200_get_final_states(m->sh[i], out + (size_t)2 * m->N * m->k_lo[i]);
+        if (rc) { m->err = m->sh[i]->err; return rc; }
+    }
+    return 0;
 }
 
 }  // extern "C"

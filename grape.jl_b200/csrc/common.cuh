@@ -95,6 +95,8 @@ struct DevFlags {
     int taylor_fail;      // != 0: taylor_grad_step did not converge
     double chi_bad_rho;
     double taylor_r;
+    int xchg_timeout;     // != 0: a peer never arrived at an exchange (xchg.cuh)
+    int pad_;
 };
 
 // Everything a kernel needs, passed by value.

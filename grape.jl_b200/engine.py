@@ -30,39 +30,45 @@ def _colmajor(mats):
     return np.ascontiguousarray(np.swapaxes(mats, -1, -2))
 
 
+def _descriptor(p: GrapeProblem, device: int, keep: dict):
+    """Fill a `grape_b200_problem` from a GrapeProblem; `keep` holds the arrays the pointers refer to."""
+    keep["tlist"] = p.tlist
+    keep["H0"] = _colmajor(p.H0)
+    keep["Hc"] = _colmajor(p.Hc)
+    keep["psi0"], keep["tgt"] = p.psi0, p.tgt
+    keep["gen"] = p.gen_of_traj
+    d = _lib.ProblemDesc()
+    d.abi_version = _lib.ABI_VERSION
+    d.K, d.N, d.L, d.NT, d.G = p.K, p.N, p.L, p.NT, p.G
+    d.K_global, d.device = p.K_global, device
+    d.tlist = _dp(keep["tlist"])
+    d.gen_of_traj = keep["gen"].ctypes.data_as(C.POINTER(C.c_int32))
+    d.H0, d.Hc = _dp(keep["H0"].view(np.float64)), _dp(keep["Hc"].view(np.float64))
+    d.shape = _dp(p.shape)
+    d.psi0, d.tgt = _dp(p.psi0.view(np.float64)), _dp(p.tgt.view(np.float64))
+    d.weights = _dp(p.weights)
+    d.functional, d.gradient_method = p.functional, p.gradient_method
+    d.ja_kind, d.gb_kind = p.ja_kind, p.gb_kind
+    d.lambda_a, d.lambda_b = p.lambda_a, p.lambda_b
+    if p.gb_D is not None and p.gb_kind:
+        keep["D"] = _colmajor(p.gb_D)
+        d.gb_D = _dp(keep["D"].view(np.float64))
+        d.gb_nD = p.gb_D.shape[0]
+    d.taylor_max_order = p.taylor_max_order
+    d.taylor_tolerance = p.taylor_tolerance
+    d.taylor_check_convergence = int(p.taylor_check_convergence)
+    d.path = p.path
+    d.chi_min_norm = p.chi_min_norm
+    return d
+
+
 class GrapeEngine:
     def __init__(self, problem: GrapeProblem, device: int = 0):
         self.lib = _lib.load()
         p = self.problem = problem
         self.K, self.N, self.L, self.NT = p.K, p.N, p.L, p.NT
         self._keep = keep = {}
-        keep["tlist"] = p.tlist
-        keep["H0"] = _colmajor(p.H0)
-        keep["Hc"] = _colmajor(p.Hc)
-        keep["psi0"], keep["tgt"] = p.psi0, p.tgt
-        keep["gen"] = p.gen_of_traj
-        d = _lib.ProblemDesc()
-        d.abi_version = _lib.ABI_VERSION
-        d.K, d.N, d.L, d.NT, d.G = p.K, p.N, p.L, p.NT, p.G
-        d.K_global, d.device = p.K_global, device
-        d.tlist = _dp(keep["tlist"])
-        d.gen_of_traj = keep["gen"].ctypes.data_as(C.POINTER(C.c_int32))
-        d.H0, d.Hc = _dp(keep["H0"].view(np.float64)), _dp(keep["Hc"].view(np.float64))
-        d.shape = _dp(p.shape)
-        d.psi0, d.tgt = _dp(p.psi0.view(np.float64)), _dp(p.tgt.view(np.float64))
-        d.weights = _dp(p.weights)
-        d.functional, d.gradient_method = p.functional, p.gradient_method
-        d.ja_kind, d.gb_kind = p.ja_kind, p.gb_kind
-        d.lambda_a, d.lambda_b = p.lambda_a, p.lambda_b
-        if p.gb_D is not None and p.gb_kind:
-            keep["D"] = _colmajor(p.gb_D)
-            d.gb_D = _dp(keep["D"].view(np.float64))
-            d.gb_nD = p.gb_D.shape[0]
-        d.taylor_max_order = p.taylor_max_order
-        d.taylor_tolerance = p.taylor_tolerance
-        d.taylor_check_convergence = int(p.taylor_check_convergence)
-        d.path = p.path
-        d.chi_min_norm = p.chi_min_norm
+        d = _descriptor(p, device, keep)
         h = C.c_void_p()
         rc = self.lib.grape_b200_create(C.byref(d), C.byref(h))
         if rc != 0:
@@ -214,3 +220,83 @@ class GrapeEngine:
 
     def stream(self):
         return self.lib.grape_b200_stream(self._h)
+
+    # -- peer exchange between shards, one process per GPU (include/grape_b200.h, csrc/xchg.cuh) -------
+    def xchg_init(self, rank, world):
+        """Allocate this shard's exchange buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        self._check(self.lib.grape_b200_xchg_init(self._h, int(rank), int(world), buf))
+        return buf.raw
+
+    def xchg_attach(self, handles):
+        """`handles`: the IPC handles of ALL ranks in rank order. Afterwards evaluate_* / enqueue_* are collective
+        calls that return the global J and gradient on every rank."""
+        blob = b"".join(handles)
+        assert len(blob) % _lib.IPC_HANDLE_BYTES == 0
+        self._check(self.lib.grape_b200_xchg_attach(self._h, C.c_char_p(blob)))
+
+    def xchg_detach(self):
+        self._check(self.lib.grape_b200_xchg_detach(self._h))
+
+
+class MultiGrapeEngine:
+    """The WHOLE problem on several GPUs driven by this one process (`grape_b200_multi_*`): same
+    `evaluate_functional` / `evaluate_gradient` surface as GrapeEngine."""
+
+    def __init__(self, problem: GrapeProblem, devices):
+        self.lib = _lib.load()
+        p = self.problem = problem
+        self.K, self.N, self.L, self.NT = p.K, p.N, p.L, p.NT
+        self._keep = {}
+        d = _descriptor(p, 0, self._keep)
+        devs = (C.c_int32 * len(devices))(*[int(x) for x in devices])
+        h = C.c_void_p()
+        rc = self.lib.grape_b200_multi_create(C.byref(d), devs, len(devices), C.byref(h))
+        if rc != 0:
+            raise GrapeError(rc, (self.lib.grape_b200_multi_last_error(None) or b"").decode())
+        self._h = h
+        LNT = p.L * p.NT
+        self.J_parts = np.zeros(3)
+        self.tau_vals = np.zeros(p.K, dtype=np.complex128)
+        self.grad_J_Tb, self.grad_J_a = np.zeros(LNT), np.zeros(LNT)
+        self.fg_calls = self.f_calls = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.grape_b200_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GrapeError(rc, (self.lib.grape_b200_multi_last_error(self._h) or b"").decode())
+
+    def size(self):
+        return int(self.lib.grape_b200_multi_size(self._h))
+
+    def evaluate_functional(self, pulsevals):
+        x = GrapeEngine._pulses(pulsevals, self.L * self.NT)
+        self._check(self.lib.grape_b200_multi_eval_f(self._h, _dp(x), _dp(self.J_parts),
+                                                     _dp(self.tau_vals.view(np.float64))))
+        self.f_calls += 1
+        return float(np.sum(self.J_parts))
+
+    def evaluate_gradient(self, G, pulsevals):
+        x = GrapeEngine._pulses(pulsevals, self.L * self.NT)
+        if not (isinstance(G, np.ndarray) and G.dtype == np.float64 and G.flags.c_contiguous and G.shape == x.shape):
+            raise ValueError("G must be a contiguous float64 array of length L*NT")
+        self._check(self.lib.grape_b200_multi_eval_fg(
+            self._h, _dp(x), _dp(G), _dp(self.J_parts), _dp(self.tau_vals.view(np.float64)),
+            _dp(self.grad_J_Tb), _dp(self.grad_J_a)))
+        self.fg_calls += 1
+        return float(np.sum(self.J_parts))
+
+    def final_states(self):
+        out = np.zeros((self.K, self.N), dtype=np.complex128)
+        self._check(self.lib.grape_b200_multi_get_final_states(self._h, _dp(out.view(np.float64))))
+        return out

@@ -62,14 +62,21 @@ def _sym_flops_per_unit(p, eps, sample=64):
     m, _ = _vec_terms(nrm)
     m = np.minimum(m, 8).astype(float)
     c_flops = np.mean(12.0 * N * N * m + 10.0 * N * m + 2.0 * N * m * (m - 1)) + 4.0 * L * N * N + N * N
-    return float(a_flops + 8.0 * N * N + c_flops)
+    return dict(formation=float(a_flops), chains=float(8.0 * N * N), contraction=float(c_flops))
 
 
-def executed_flops_per_unit(p, eps, sample=64, schedule=None):
-    """schedule = GrapeEngine.small_schedule() of the measured call (3: real-symmetric kernels)."""
+def executed_flops_split(p, eps, sample=64, schedule=None):
+    """Executed FP64 flops per unit by kernel group: propagator formation (+ segment products), the boundary chains /
+    segment fills, the gradient contraction (which carries chi -- and Psi on the Hermitian schedules -- backwards).
+    schedule = GrapeEngine.small_schedule() of the measured call (3: real-symmetric kernels)."""
     if schedule == 3:
         return _sym_flops_per_unit(p, eps, sample)
     return _general_flops_per_unit(p, eps, sample)
+
+
+def executed_flops_per_unit(p, eps, sample=64, schedule=None):
+    d = executed_flops_split(p, eps, sample, schedule)
+    return d["formation"] + d["chains"] + d["contraction"]
 
 
 def _general_flops_per_unit(p, eps, sample=64):
@@ -102,7 +109,7 @@ def _general_flops_per_unit(p, eps, sample=64):
     b_flops = 2 * 8.0 * N * N          # forward fill / chain + backward fill / chain mat-vecs
     if seg and N <= 4:
         b_flops = 8.0 * N * N          # chi is carried inside the contraction kernel
-    return float(a_flops + b_flops + c_flops)
+    return dict(formation=float(a_flops), chains=float(b_flops), contraction=float(c_flops))
 
 
 def dense_flops_per_unit(p, eps, form=0):

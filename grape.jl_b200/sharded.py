@@ -9,8 +9,15 @@ the sum over k):
      after the forward sweep;
   2. all-reduce(sum) of the partial gradient [L*NT] after the backward sweep.
 For J_T_re / J_T_ss chi_k does not depend on the other trajectories, so (1) is only
-needed for the value of J and travels with (2) in one coalesced NCCL call.
-The host-side optimizer step is unchanged and identical on every rank."""
+needed for the value of J and travels with (2).
+
+Default exchange ("p2p"): the library's own reduction kernels push the partials into
+every peer's exchange buffer over NVLink and add them in rank order (csrc/xchg.cuh) --
+`torch.distributed` is only used ONCE, at set-up, to pass the 64-byte CUDA IPC handles
+around; there is no collective-library launch and no Python between the kernels of a
+step.  exchange="nccl" keeps the in-place NCCL all-reduces of round 1 (comparison /
+boxes without peer access).  The host-side optimizer step is unchanged and identical
+on every rank."""
 from __future__ import annotations
 
 import numpy as np
@@ -24,7 +31,7 @@ class ShardedGrape:
     GrapeEngine in production).  Collectives run on `device` tensors when given
     (NCCL) or on CPU tensors (gloo)."""
 
-    def __init__(self, problem, engine_factory, rank=None, world=None, device=None, group=None):
+    def __init__(self, problem, engine_factory, rank=None, world=None, device=None, group=None, exchange="p2p"):
         import torch
         import torch.distributed as dist
         self._torch, self._dist, self.group = torch, dist, group
@@ -43,7 +50,7 @@ class ShardedGrape:
         self._pipe = None
         if device is not None and getattr(device, "type", "cpu") == "cuda" and hasattr(self.engine, "enqueue_forward"):
             dd = dist if self.world > 1 else None
-            self._pipe = DevicePipeline(self.engine, dd, group)
+            self._pipe = DevicePipeline(self.engine, dd, group, exchange=exchange)
             self._stream = torch.cuda.ExternalStream(self.engine.stream(), device=device)
             self._h_eps = torch.empty(LNT, dtype=torch.float64).pin_memory()
             self._d_eps = torch.empty(LNT, dtype=torch.float64, device=device)
@@ -60,6 +67,7 @@ class ShardedGrape:
         is freed, so they must go before `grape_b200_destroy` destroys that stream."""
         if self._pipe is not None:
             self.engine.finish()
+            self._pipe.close()
             self._h_eps = self._h_out = self._d_eps = self._J_t = None
             self._pipe = None
             self._stream = None
@@ -79,6 +87,14 @@ class ShardedGrape:
 
     def evaluate_gradient(self, G, pulsevals):
         e = self.engine
+        if self._pipe is not None and self._pipe.exchange == "p2p":
+            # peers attached: the blocking C-ABI call IS the sharded evaluation (one graph launch per rank, the
+            # exchanges happen inside its kernels); every rank gets the global J and gradient
+            J = e.evaluate_gradient(G, pulsevals)
+            self.J_parts[:] = e.J_parts
+            self.grad_J_Tb[:] = e.grad_J_Tb
+            self.grad_J_a[:] = e.grad_J_a
+            return J
         if self._pipe is not None:
             t = self._torch
             LNT = G.shape[0]
@@ -104,6 +120,10 @@ class ShardedGrape:
         return float(np.sum(self.J_parts))
 
     def evaluate_functional(self, pulsevals):
+        if self._pipe is not None and self._pipe.exchange == "p2p":
+            J = self.engine.evaluate_functional(pulsevals)
+            self.J_parts[:] = self.engine.J_parts
+            return J
         # forward only; J_T from the reduced sums (same formulas as finalize_J)
         p = self.problem
         sums = self._allreduce(self._sums, self.engine.forward(pulsevals))
@@ -137,7 +157,7 @@ class DevicePipeline:
 
     Call `step()` under `torch.cuda.stream(torch.cuda.ExternalStream(engine.stream()))`."""
 
-    def __init__(self, engine, dist=None, group=None):
+    def __init__(self, engine, dist=None, group=None, exchange="p2p"):
         import torch
         self.engine, self.dist, self.group = engine, dist, group
         LNT = engine.L * engine.NT
@@ -147,11 +167,43 @@ class DevicePipeline:
         self.G_t = torch.as_tensor(_DevArray(engine.device_ptr(3), LNT), device=dev)
         # J_T_sm: chi_k is proportional to sum_j tau_j (reference docs/src/tutorial.md:399-405), so the backward sweep
         # needs the global sums. J_T_re / J_T_ss: chi_k only depends on tau_k, the sums are needed for J alone, and
-        # both exchanges travel in ONE coalesced NCCL call after the backward sweep.
+        # both exchanges travel together after the backward sweep.
         self.coupled = int(getattr(engine.problem, "functional", 0)) == 0
         self.coalesce = False
-        if dist is not None and not self.coupled:
-            self.coalesce = self._probe_coalescing(torch, dev)
+        self.exchange = "none"
+        self.exchange_note = ""
+        if dist is not None:
+            self.exchange = exchange
+            if exchange == "p2p" and not self._attach_peers(torch, dev):
+                self.exchange = "nccl"
+            if self.exchange == "nccl" and not self.coupled:
+                self.coalesce = self._probe_coalescing(torch, dev)
+
+    def _attach_peers(self, torch, dev):
+        """Pass the IPC handles of the shards' exchange buffers around (the only use of torch.distributed) and map
+        them. All ranks must end up on the same path: if any rank cannot map its peers, every rank falls back to NCCL
+        (recorded in `exchange_note`, reported by bench.py)."""
+        d = self.dist
+        rank, world = d.get_rank(self.group), d.get_world_size(self.group)
+        ok, note = 1.0, ""
+        try:
+            mine = self.engine.xchg_init(rank, world)
+            handles = [None] * world
+            d.all_gather_object(handles, mine, group=self.group)
+            self.engine.xchg_attach(handles)
+        except Exception as exc:          # GrapeError (no peer access / IPC refused) or a failed gather
+            ok, note = 0.0, str(exc)
+        flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+        d.all_reduce(flag, op=d.ReduceOp.MIN, group=self.group)
+        if flag.item() != 1.0:
+            try:
+                self.engine.xchg_detach()
+            except Exception:
+                pass
+            self.exchange_note = "p2p attach failed on some rank -> nccl" + (f" ({note})" if note else "")
+            return False
+        d.barrier(group=self.group)
+        return True
 
     def _probe_coalescing(self, torch, dev):
         """one coalesced all-reduce of two scratch tensors on every rank: usable iff it returns the right sums"""
@@ -172,6 +224,10 @@ class DevicePipeline:
 
     def step(self, d_eps):
         e, d = self.engine, self.dist
+        if self.exchange == "p2p":        # exchanges inside the library's kernels (NVLink peer stores)
+            e.enqueue_forward(d_eps.data_ptr())
+            e.enqueue_backward()
+            return
         e.enqueue_forward(d_eps.data_ptr())
         if d is not None and self.coupled:
             d.all_reduce(self.sums_t, op=d.ReduceOp.SUM, group=self.group)
@@ -190,6 +246,14 @@ class DevicePipeline:
 
     def finish(self):
         self.engine.finish()
+
+    def close(self):
+        """Unmap the peers' exchange buffers (after a barrier: no rank may still be pushing into ours)."""
+        if self.exchange == "p2p" and self.dist is not None:
+            self.engine.finish()
+            self.dist.barrier(group=self.group)
+            self.engine.xchg_detach()
+            self.exchange = "none"
 
     def gradient(self):
         return self.G_t

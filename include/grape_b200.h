@@ -29,6 +29,18 @@
  *
  * One handle = one CUDA device = one shard of trajectories.  A handle is not
  * re-entrant; distinct handles are independent.
+ *
+ * Several GPUs (the reference parallelises the same axis with threads: `@threadsif`
+ * over k, src/optimize.jl:720, 876): contiguous blocks of trajectories, one shard per
+ * GPU.  The only couplings -- the functional / chi (all tau_k, src/optimize.jl:755-760,
+ * 845-855) and the sum over k (src/optimize.jl:574-584) -- are reduced BY THE LIBRARY'S
+ * OWN KERNELS over NVLink peer memory (csrc/xchg.cuh), either
+ *   - in one host process:   grape_b200_multi_create(desc, devices, ndev) + grape_b200_multi_eval_fg
+ *     (what a Julia host calls), or
+ *   - one process per GPU:   grape_b200_create(local shard) on every rank, grape_b200_xchg_init ->
+ *     exchange the 64-byte IPC handles by any means -> grape_b200_xchg_attach; then eval_f / eval_fg /
+ *     eval_fg_device / enqueue_* return the GLOBAL J and gradient on every rank (collective calls:
+ *     every rank makes the same sequence).
  */
 #ifndef GRAPE_B200_H
 #define GRAPE_B200_H
@@ -49,7 +61,7 @@ extern "C" {
 #define GRAPE_B200_ETAYLOR       4  /* taylor_grad_step! did not converge (src/optimize.jl:644-648) */
 #define GRAPE_B200_ENOCONTROLS   5  /* "no controls in trajectories" (src/workspace.jl:155-157) */
 #define GRAPE_B200_ESTATE        6  /* call sequence error (backward before forward, ...)  */
-#define GRAPE_B200_ENCCL         7  /* NCCL failure                                       */
+#define GRAPE_B200_ENCCL         7  /* multi-GPU exchange failure (no peer access, IPC, a shard never arrived) */
 
 /* J_T / chi kind: QuantumControl.Functionals J_T_sm / J_T_re / J_T_ss with their
  * analytic chi (make_chi, src/workspace.jl:306-308); HOST = arbitrary closures,
@@ -211,6 +223,37 @@ int grape_b200_gradient_form(grape_b200_handle* h);
  *   3 = time-segmented, real-symmetric generators (same as 2 in real matrix arithmetic, csrc/small_sym.cuh).
  * All evaluate src/optimize.jl:824-1014 with the same truncation. Negative: error code. */
 int grape_b200_small_schedule(grape_b200_handle* h);
+
+/* ---- multi-GPU: peer exchange between shards, one process per GPU -------------------------------------
+ * grape_b200_xchg_init allocates this shard's exchange buffer for `world` shards (this one is `rank`) and
+ * returns its cudaIpcMemHandle_t (64 bytes) in ipc_handle_out (may be NULL when all shards live in one
+ * process).  grape_b200_xchg_attach takes the handles of ALL ranks, [world][64] bytes in rank order, maps the
+ * peers' buffers (cudaIpcOpenMemHandle, NVLink/NVSwitch P2P) and switches the evaluation entry points to the
+ * sharded form: the k-reduction kernel pushes its partial gradient into every peer's buffer and every rank
+ * adds the world partials in rank order (bit-identical on all ranks, no NCCL, no host in the step).
+ * The split host API (grape_b200_forward / _backward / _backward_chi) keeps returning LOCAL partials. */
+#define GRAPE_B200_IPC_HANDLE_BYTES 64
+int grape_b200_xchg_init(grape_b200_handle* h, int32_t rank, int32_t world, void* ipc_handle_out);
+int grape_b200_xchg_attach(grape_b200_handle* h, const void* ipc_handles);
+int grape_b200_xchg_detach(grape_b200_handle* h);
+
+/* ---- multi-GPU: one host process, several devices (reference: one Julia process, src/optimize.jl:720) --
+ * `desc` describes the WHOLE problem (desc->device is ignored); trajectories are split into ndev contiguous
+ * blocks, block i on devices[i] (generators unused by a block are not uploaded there).  multi_eval_f /
+ * multi_eval_fg = evaluate_functional / evaluate_gradient! of the whole ensemble: one H2D copy of the pulse
+ * values per device, all devices run concurrently and meet in the exchange kernels, the result is read from
+ * device 0 (tau [2*K] is gathered from all shards). */
+typedef struct grape_b200_multi grape_b200_multi;
+int  grape_b200_multi_create(const grape_b200_problem* desc, const int32_t* devices, int32_t ndev, grape_b200_multi** out);
+void grape_b200_multi_destroy(grape_b200_multi* m);
+const char* grape_b200_multi_last_error(const grape_b200_multi* m);   /* m == NULL: last failed multi_create */
+int  grape_b200_multi_eval_f(grape_b200_multi* m, const double* pulsevals, double* J_parts, double* tau);
+int  grape_b200_multi_eval_fg(grape_b200_multi* m, const double* pulsevals, double* G, double* J_parts,
+                              double* tau, double* grad_J_Tb, double* grad_J_a);
+int  grape_b200_multi_get_final_states(grape_b200_multi* m, double* out /* [K][N] complex */);
+int32_t grape_b200_multi_size(const grape_b200_multi* m);
+/* shard i (for the per-shard read-backs above); *k_first = index of its first trajectory */
+grape_b200_handle* grape_b200_multi_shard(grape_b200_multi* m, int32_t i, int32_t* k_first);
 
 #ifdef __cplusplus
 }

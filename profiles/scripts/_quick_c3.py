@@ -1,6 +1,6 @@
 """timing helper (not a test): C3 gradient time against the segment length (GRAPE_B200_SEG_S; 0 = automatic)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from grape.jl_b200 import configs
 from grape.jl_b200.engine import GrapeEngine

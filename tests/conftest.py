@@ -12,6 +12,34 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_present():
+    """True iff the CUDA runtime sees a device (no torch import: the check must stay cheap)."""
+    import ctypes
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+        try:
+            rt = ctypes.CDLL(name)
+        except OSError:
+            continue
+        n = ctypes.c_int(0)
+        return rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 and n.value > 0
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not failed) on a host without a CUDA device, so a plain `pytest tests` is green on the
+    CPU-only container; on the GPU box nothing is skipped and the engine fails loudly if its library is missing."""
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this host (gpu-marked test)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def lib_built():
     """Build the shared library once per session (nvcc cross-compiles without a GPU)."""

@@ -62,3 +62,30 @@ class OracleEngine:
         if self.op.gb_kind:
             self.J_parts[2] = self.op.lambda_b * sums_global[3]
         return self.J_parts.copy()
+
+
+class COracleEngine(OracleEngine):
+    """Same surface, backed by the OpenMP C restatement (oracle/grape_oracle_c.c): for host-loop tests whose
+    problems are too large for the Python loops (GradGenerator path, built-in functionals)."""
+
+    def _run(self, x, want_grad):
+        from oracle import c_oracle as co
+        r = co.evaluate_gradient(self.problem, x, want_grad=want_grad)
+        assert r["rc"] == 0
+        r["final_states"] = r["storage"][:, -1, :].copy()
+        self._last = r
+        self.J_parts[:] = r["J_parts"]
+        self.tau_vals[:] = r["tau"]
+        return r
+
+    def evaluate_functional(self, x):
+        return self._run(x, False)["J"]
+
+    def evaluate_gradient(self, G, x):
+        r = self._run(x, True)
+        G[:] = r["G"]
+        dt = np.diff(self.problem.tlist)
+        ga = (2.0 * np.asarray(x).reshape(self.L, self.NT) * dt[None, :]).reshape(-1) if self.problem.ja_kind else 0.0
+        self.grad_J_a[:] = ga
+        self.grad_J_Tb[:] = r["G"] - (self.problem.lambda_a * ga if self.problem.ja_kind else 0.0)
+        return r["J"]

@@ -81,3 +81,24 @@ def _lambda_ensemble():
 def test_ensemble_with_running_costs(lib_built):
     D = np.diag([0.0, 1.0, 0.0])
     _both(_lambda_ensemble, J_T=J_T_ss, J_a=J_a_fluence, lambda_a=0.01, g_b=QuadraticForm(D), lambda_b=0.2)
+
+
+def test_cnot_saddle_point_on_gpu(lib_built):
+    """The reference's RNG-free CNOT pin (test/test_lbfgsb_saddle_point.jl:89-124) through the CUDA engine (K=4, N=4,
+    L=6, NT=1000): stalls at the J_T = 0.75 saddle with loose L-BFGS-B tolerances, passes it with the defaults; and
+    the GPU-driven run follows the oracle-driven run (same iteration count, J_T to 1e-8) while it sits on the saddle."""
+    from tests.oracle_engine import COracleEngine
+    from tests.saddle_fixture import cnot_trajectories
+    tr, tl = cnot_trajectories()
+    g = optimize(tr, tl, J_T=J_T_sm, iter_stop=50, lbfgsb_pgtol=1e-5, lbfgsb_factr=1e7)
+    assert not g.converged
+    assert "NORM OF PROJECTED GRADIENT <= PGTOL" in g.message.replace("_", " ")
+    assert abs(g.J_T - 0.75) < 1e-3
+    tr, tl = cnot_trajectories()
+    c = optimize(tr, tl, J_T=J_T_sm, iter_stop=50, lbfgsb_pgtol=1e-5, lbfgsb_factr=1e7, engine_factory=COracleEngine)
+    assert g.iter == c.iter and abs(g.J_T - c.J_T) < 1e-8
+    for a, b in zip(g.optimized_controls, c.optimized_controls):
+        assert np.max(np.abs(a - b)) <= PULSE_TOL * max(1.0, np.max(np.abs(b)))
+    tr, tl = cnot_trajectories()
+    g = optimize(tr, tl, J_T=J_T_sm, iter_stop=50)
+    assert g.converged and g.J_T < 1e-2

@@ -237,3 +237,20 @@ def test_gradient_against_richardson_extrapolated_differences(functional, hermit
         a, b, c = d1(i, 0.04), d1(i, 0.02), d1(i, 0.01)
         r2 = (16 * (4 * c - b) / 3 - (4 * b - a) / 3) / 15
         assert abs(r2 - r["G"][i]) <= 1e-11 * scale, (i, r2, r["G"][i])
+
+
+def test_cnot_saddle_point_fixture():
+    """test/test_lbfgsb_saddle_point.jl:89-124 (RNG-free): with the old 'medium precision' L-BFGS-B settings the
+    optimization stalls on the saddle at J_T = 0.75 with the PGTOL message; with the defaults it reaches J_T < 1e-2
+    within the 50 iterations.  Runs the host loop (nbd = 3, u = +Inf encoding) on the C restatement of the oracle."""
+    from grape.jl_b200.optimize import optimize, J_T_sm
+    from tests.oracle_engine import COracleEngine
+    from tests.saddle_fixture import cnot_trajectories
+    tr, tl = cnot_trajectories()
+    r = optimize(tr, tl, J_T=J_T_sm, iter_stop=50, lbfgsb_pgtol=1e-5, lbfgsb_factr=1e7, engine_factory=COracleEngine)
+    assert not r.converged                                                       # :116
+    assert "NORM OF PROJECTED GRADIENT <= PGTOL" in r.message.replace("_", " ")   # :117
+    assert abs(r.J_T - 0.75) < 1e-3                                              # :118
+    tr, tl = cnot_trajectories()
+    r = optimize(tr, tl, J_T=J_T_sm, iter_stop=50, engine_factory=COracleEngine)
+    assert r.converged and r.J_T < 1e-2                                          # :121-122

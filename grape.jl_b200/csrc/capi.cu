@@ -66,6 +66,7 @@ struct grape_b200_handle_impl {
                           // the forward states backwards; fw_storage is only filled when somebody reads it
     bool U_valid;         // small path: p.U holds the propagators of the current pulses
     bool seg_fuse;        // small path, segmented: fused propagator formation + segment product (small_formseg)
+    int sym_v;            // 2: operators staged in shared memory (small_*_sym2, default); 1: round-1 kernels (GRAPE_B200_SYM_V=1)
     int sym_occ;          // resident CTAs per SM small_seggrad_sym is compiled for (3; GRAPE_B200_SYM_OCC=2: no spills, 8 warps)
     bool seg_real;        // seg_herm and every generator real (symmetric): real-arithmetic kernels of small_sym.cuh
     cplx* d_taugrads;     // [K][L][NT] dump buffer of get_tau_grads (allocated on first use)
@@ -228,6 +229,23 @@ int small_setup(H* h, const grape_b200_problem* d) {
             for (size_t e = 0; e < (size_t)G * L * NN && real; ++e) real = d->Hc[2 * e + 1] == 0.0;
             h->seg_real = real;
             h->sym_occ = getenv("GRAPE_B200_SYM_OCC") ? atoi(getenv("GRAPE_B200_SYM_OCC")) : 3;
+            h->sym_v = getenv("GRAPE_B200_SYM_V") ? atoi(getenv("GRAPE_B200_SYM_V")) : 2;
+            if (getenv("GRAPE_B200_SYM_OCC")) h->sym_v = 1;   // the occupancy variants exist for the round-1 kernels only
+            if (real && h->sym_v != 1) {
+                // per-thread operator tile of the staged kernels: (1 + L) N^2 doubles x 128 threads
+                const size_t sm = sym_stage_bytes(N, L);
+                if (sm > 96 * 1024) h->sym_v = 1;
+                else if (sm > 48 * 1024) {
+                    cudaError_t e = cudaSuccess;
+                    auto set = [&](const void* fn) { if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); };
+                    switch (N) {
+                        case 1: set((const void*)small_formseg_sym2<1, 0>); set((const void*)small_seggrad_sym2<1, 0>); break;
+                        case 2: set((const void*)small_formseg_sym2<2, 0>); set((const void*)small_seggrad_sym2<2, 0>); break;
+                        default: set((const void*)small_formseg_sym2<3, 0>); set((const void*)small_seggrad_sym2<3, 0>); break;
+                    }
+                    if (e != cudaSuccess) { cudaGetLastError(); h->sym_v = 1; }
+                }
+            }
             if (real) {
                 std::vector<double> rb((size_t)NN * G);
                 for (int g = 0; g < G; ++g)
@@ -344,8 +362,14 @@ template <int N>
 void seg_formseg_t(H* h) {
     const long long tot = (long long)h->p.G * h->seg.NSEG;
     if (N <= 3 && h->seg_real) {
+        constexpr int NS = N <= 3 ? N : 1;
         cudaMemsetAsync(h->seg.notfast, 0, sizeof(int), h->stream);
-        small_formseg_sym<(N <= 3 ? N : 1)><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+        const unsigned blocks = (unsigned)((tot + SYM_BD - 1) / SYM_BD);
+        const size_t sm = sym_stage_bytes(N, h->p.L);
+        if (h->sym_v == 1) small_formseg_sym<NS><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+        else if (h->p.L == 1) small_formseg_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
+        else if (h->p.L == 2) small_formseg_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
+        else small_formseg_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
     } else {
         small_formseg<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
     }
@@ -398,8 +422,15 @@ void seg_grad_t(H* h) {
         const SegArgs& a = h->seg;
         const int SPW = 32 / a.BKL;
         const long long warps = (long long)((h->p.K + a.BKL - 1) / a.BKL) * ((a.NSEG + SPW - 1) / SPW);
-        if (h->sym_occ == 2) small_seggrad_sym<(N <= 3 ? N : 1), 2><<<(unsigned)((warps + 3) / 4), 128, 0, h->stream>>>(h->p, a);
-        else small_seggrad_sym<(N <= 3 ? N : 1), 3><<<(unsigned)((warps + 3) / 4), 128, 0, h->stream>>>(h->p, a);
+        constexpr int NS = N <= 3 ? N : 1;
+        const unsigned blocks = (unsigned)((warps + 3) / 4);
+        const size_t sm = sym_stage_bytes(N, h->p.L);
+        if (h->sym_v == 1) {   // round-1 kernels (operators re-loaded from global memory every step)
+            if (h->sym_occ == 2) small_seggrad_sym<NS, 2><<<blocks, 128, 0, h->stream>>>(h->p, a);
+            else small_seggrad_sym<NS, 3><<<blocks, 128, 0, h->stream>>>(h->p, a);
+        } else if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+        else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+        else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
         h->launches++;
         run_if = a.notfast;
     }
@@ -749,7 +780,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->taugrads_valid = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
-    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->d_taugrads = nullptr; h->taugrads_valid = false;
+    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->d_taugrads = nullptr; h->taugrads_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     memset(&h->xd, 0, sizeof h->xd); h->xchg_on = false; h->xchg_mode = false; h->xchg_fonly = false;
     h->xchg_buf = nullptr; h->xchg_bytes = 0; h->launched_via_graph = false; h->launch_l0 = 0;

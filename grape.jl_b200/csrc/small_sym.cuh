@@ -312,3 +312,229 @@ __global__ void __launch_bounds__(128, MINB) small_seggrad_sym(DevP p, SegArgs a
         }
     }
 }
+
+// ===========================================================================================
+// Round 2: the same two kernels with the thread's generator staged ONCE in shared memory.
+//
+// ncu / SASS of the kernels above (profiles/r1_s11_ncu_full_c3_sym_raw.csv): FP64 pipe 54-57 % active, but
+// only ~60 % of the issued instructions are DFMA/DMUL -- every step re-loads the 9 (1 + L) real operator
+// elements of the thread's generator through 64-bit address arithmetic (IMAD/LEA/IADD3 + LDG: ~170
+// instructions per control and step, twice in the gradient kernel: Hs formation and the traces).  The
+// operators do not depend on the step: each thread copies them once into its own column of a shared-memory
+// tile sH[c][tid] (conflict-free, addressed by immediates), and the number of controls is a template
+// parameter (LT = 1, 2; 0 = run-time L) so the per-control loops unroll.  Same arithmetic, same order of
+// operations per element, hence bit-identical results to the kernels above.
+// ===========================================================================================
+constexpr int SYM_BD = 128;   // threads per block of the staged kernels
+
+// dynamic shared memory of the staged kernels, bytes
+inline size_t sym_stage_bytes(int N, int L) { return (size_t)(1 + L) * N * N * SYM_BD * sizeof(double); }
+
+template <int N>
+GB_D void sym_stage(const DevP& p, const SegArgs& a, int g, int L, double* sH) {
+    constexpr int NN = N * N;
+    const int G = p.G, t = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) sH[c * SYM_BD + t] = __ldg(&a.H0r[(size_t)c * G + g]);
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+        for (int c = 0; c < NN; ++c) sH[(NN + l * NN + c) * SYM_BD + t] = __ldg(&a.Hcr[((size_t)l * NN + c) * G + g]);
+}
+
+// Hs = H0 + sum_l a_l Hc_l from the staged tile, and its 1-norm
+template <int N, int LT>
+GB_D double sym_form_H_staged(const DevP& p, const double* sH, int L, int n, double (&Hs)[N * N]) {
+    constexpr int NN = N * N;
+    const int NT = p.NT, t = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Hs[c] = sH[c * SYM_BD + t];
+    if (LT > 0) {
+#pragma unroll
+        for (int l = 0; l < LT; ++l) {
+            double am = p.eps[l * NT + n];
+            if (p.shape) am *= p.shape[l * NT + n];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * SYM_BD + t], Hs[c]);
+        }
+    } else {
+        for (int l = 0; l < L; ++l) {
+            double am = p.eps[l * NT + n];
+            if (p.shape) am *= p.shape[l * NT + n];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * SYM_BD + t], Hs[c]);
+        }
+    }
+    double nrm = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
+        nrm = fmax(nrm, s);
+    }
+    return nrm;
+}
+
+// U_n = cos(Hs) - i sin(Hs) of one step (Hs unscaled generator, theta = dt * ||Hs||_1), as in small_formseg_sym
+template <int N>
+GB_D void sym_cos_sin(double (&Hs)[N * N], double dt, double theta, double (&Cm)[N * N], double (&Sm)[N * N]) {
+    constexpr int NN = N * N;
+    int degree, s;
+    exp_plan(theta, degree, s);
+    const double sc = s > 0 ? dt * ldexp(1.0, -s) : dt;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Hs[c] *= sc;
+    double Q[NN];
+    rm_mm<N>(Q, Hs, Hs);
+    const int d2 = (degree - 1) / 2;
+    double Sp[NN];
+    {
+        const double sg = (d2 & 1) ? -1.0 : 1.0;
+        const double c1 = sg * c_invfact[2 * d2], c0 = -sg * c_invfact[2 * d2 - 2];
+        const double s1 = sg * c_invfact[2 * d2 + 1], s0 = -sg * c_invfact[2 * d2 - 1];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) { Cm[c] = c1 * Q[c]; Sp[c] = s1 * Q[c]; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Cm[i * N + i] += c0; Sp[i * N + i] += s0; }
+    }
+    for (int j = d2 - 2; j >= 0; --j) {
+        const double sg = (j & 1) ? -1.0 : 1.0;
+        const double cj = sg * c_invfact[2 * j], sj = sg * c_invfact[2 * j + 1];
+        double T1[NN], T2[NN];
+        rm_mm<N>(T1, Q, Cm);
+        rm_mm<N>(T2, Q, Sp);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) { Cm[c] = T1[c]; Sp[c] = T2[c]; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Cm[i * N + i] += cj; Sp[i * N + i] += sj; }
+    }
+    rm_mm<N>(Sm, Hs, Sp);
+    for (int t = 0; t < s; ++t) {   // (C - iS)^2 = (C^2 - S^2) - i (2 S C)
+        double T1[NN], T2[NN], T3[NN];
+        rm_mm<N>(T1, Cm, Cm);
+        rm_mm<N>(T2, Sm, Sm);
+        rm_mm<N>(T3, Sm, Cm);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) { Cm[c] = T1[c] - T2[c]; Sm[c] = 2.0 * T3[c]; }
+    }
+}
+
+template <int N, int LT>
+__global__ void __launch_bounds__(SYM_BD, 3) small_formseg_sym2(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    extern __shared__ double sH[];
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int G = p.G, NT = p.NT, L = LT > 0 ? LT : p.L;
+    if (idx >= (long long)G * a.NSEG) return;
+    const int g = (int)(idx % G), seg = (int)(idx / G);
+    const int n0 = seg * a.S, n1 = min(NT, n0 + a.S);
+    sym_stage<N>(p, a, g, L, sH);
+    double Pr[NN], Pi[NN];
+    for (int n = n0; n < n1; ++n) {
+        const double dt = p.tlist[n + 1] - p.tlist[n];
+        double Hs[NN];
+        const double theta = dt * sym_form_H_staged<N, LT>(p, sH, L, n, Hs);
+        if (theta > c_sym_th[SEG_MMAX]) *a.notfast = 1;   // the gradient kernel of this file cannot serve this step
+        double Cm[NN], Sm[NN];
+        sym_cos_sin<N>(Hs, dt, theta, Cm, Sm);
+        if (n == n0) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
+        } else {   // (C - iS)(Pr + i Pi)
+            double Tr[NN], Ti[NN];
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double ar = 0.0, ai = 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        ar = fma(Cm[i * N + k], Pr[k * N + j], ar);
+                        ar = fma(Sm[i * N + k], Pi[k * N + j], ar);
+                        ai = fma(Cm[i * N + k], Pi[k * N + j], ai);
+                        ai = fma(-Sm[i * N + k], Pr[k * N + j], ai);
+                    }
+                    Tr[i * N + j] = ar;
+                    Ti[i * N + j] = ai;
+                }
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Tr[c]; Pi[c] = Ti[c]; }
+        }
+    }
+    cplx* o = a.Pseg + (size_t)seg * NN * G + g;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) o[(size_t)c * G] = mk(Pr[c], Pi[c]);
+}
+
+template <int N, int LT>
+__global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    extern __shared__ double sH[];
+    if (*a.notfast) return;   // uniform over the grid: small_seggrad<N, LC, true> serves this call
+    const int K = p.K, NT = p.NT, L = LT > 0 ? LT : p.L;
+    const int lane = threadIdx.x & 31;
+    const int BKL = a.BKL, SPW = 32 / BKL;
+    const int KGR = (K + BKL - 1) / BKL;
+    const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int SGR = (a.NSEG + SPW - 1) / SPW;
+    if (wid >= (long long)KGR * SGR) return;
+    const int kg = (int)(wid % KGR), sg = (int)(wid / KGR);
+    const int tk = lane % BKL, ts = lane / BKL;
+    const int k = kg * BKL + tk, seg = sg * SPW + ts;
+    const bool live = (k < K) && (seg < a.NSEG);
+    const int kk = k < K ? k : K - 1;
+    const int sseg = seg < a.NSEG ? seg : a.NSEG - 1;
+    const int n0 = sseg * a.S, n1 = min(NT, n0 + a.S);
+    const double rho = p.rho[kk];
+    sym_stage<N>(p, a, p.gen[kk], L, sH);
+
+    cplx chi[N], psi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        chi[i] = a.chiE[((size_t)sseg * N + i) * K + kk];
+        psi[i] = ld_cs(&p.psi[((size_t)n1 * N + i) * K + kk]);   // segment boundary written by the forward chain
+    }
+    double* const part = p.partial + (size_t)kg * L * NT;
+    const bool writer = tk == 0 && seg < a.NSEG;
+    for (int st = 0; st < a.S; ++st) {   // uniform trip count across the warp
+        const int n = n1 - 1 - st;
+        const bool act = live && n >= n0;
+        const int nn = n >= n0 ? n : n0;
+        const double dt = p.tlist[nn + 1] - p.tlist[nn];
+        double Hs[NN];
+        const double theta = dt * sym_form_H_staged<N, LT>(p, sH, L, nn, Hs);
+        int m = 2;
+#pragma unroll
+        for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;
+        m = __reduce_max_sync(0xffffffffu, m);   // more orders never hurt: one uniform branch per warp
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Hs[c] *= dt;
+        double IM[NN];
+        switch (m) {
+            case 2: sym_step<N, 2>(Hs, psi, chi, IM); break;
+            case 3: sym_step<N, 3>(Hs, psi, chi, IM); break;
+            case 4: sym_step<N, 4>(Hs, psi, chi, IM); break;
+            case 5: sym_step<N, 5>(Hs, psi, chi, IM); break;
+            case 6: sym_step<N, 6>(Hs, psi, chi, IM); break;
+            case 7: sym_step<N, 7>(Hs, psi, chi, IM); break;
+            default: sym_step<N, 8>(Hs, psi, chi, IM); break;
+        }
+        auto one_control = [&](int l) {
+            double sl = dt * rho;
+            if (p.shape) sl *= p.shape[l * NT + nn];
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < NN; ++c) acc = fma(sH[(NN + l * NN + c) * SYM_BD + threadIdx.x], IM[c], acc);
+            double red = act ? sl * acc : 0.0;
+            // fixed-order sum over the BKL trajectories of this lane group
+            for (int off = BKL >> 1; off > 0; off >>= 1) red += __shfl_down_sync(0xffffffffu, red, off, BKL);
+            if (writer && n >= n0) part[(size_t)l * NT + n] = red;
+        };
+        if (LT > 0) {
+#pragma unroll
+            for (int l = 0; l < LT; ++l) one_control(l);
+        } else {
+            for (int l = 0; l < L; ++l) one_control(l);
+        }
+    }
+}

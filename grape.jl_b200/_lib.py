@@ -63,6 +63,7 @@ SYMBOLS = {
     "grape_b200_launch_count": (C.c_int64, [_P]),
     "grape_b200_gradient_form": (C.c_int, [_P]),
     "grape_b200_small_schedule": (C.c_int, [_P]),
+    "grape_b200_dense_concurrent": (C.c_int, [_P]),
     "grape_b200_xchg_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "grape_b200_xchg_attach": (C.c_int, [_P, _P]),
     "grape_b200_xchg_detach": (C.c_int, [_P]),

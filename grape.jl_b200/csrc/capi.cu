@@ -66,6 +66,8 @@ struct grape_b200_handle_impl {
                           // the forward states backwards; fw_storage is only filled when somebody reads it
     bool U_valid;         // small path: p.U holds the propagators of the current pulses
     bool seg_fuse;        // small path, segmented: fused propagator formation + segment product (small_formseg)
+    bool seg_scan;        // small path, real-symmetric generators: prefix products by a parallel scan, no boundary chains
+    bool bounds_done;     // scan schedule: the segment boundaries of fw_storage hold the states of the current pulses
     int sym_v;            // 2: operators staged in shared memory (small_*_sym2, default); 1: round-1 kernels (GRAPE_B200_SYM_V=1)
     int sym_occ;          // resident CTAs per SM small_seggrad_sym is compiled for (3; GRAPE_B200_SYM_OCC=2: no spills, 8 warps)
     bool seg_real;        // seg_herm and every generator real (symmetric): real-arithmetic kernels of small_sym.cuh
@@ -293,14 +295,33 @@ int small_setup(H* h, const grape_b200_problem* d) {
                 }
             }
         }
+        // enough (generator, segment) pairs to fill the GPU: one thread forms the propagators of its segment and their
+        // product; GRAPE_B200_NO_FORMSEG=1 / GRAPE_B200_FORCE_FORMSEG=1 override the size rule (tests)
+        h->seg_fuse = (long long)G * ((NT + S - 1) / S) >= 32768;
+        // the scan schedule below runs one block of up to 128 segment threads per generator: worthwhile from 64 generators
+        // on (a 512-trajectory shard of the C3 ensemble on 8 GPUs must not drop to the unfused kernels)
+        if (h->seg_real && h->sym_v != 1 && G >= 64 && NT >= 64) h->seg_fuse = true;
+        if (getenv("GRAPE_B200_FORCE_FORMSEG") && atoi(getenv("GRAPE_B200_FORCE_FORMSEG")) != 0) h->seg_fuse = true;
+        if (getenv("GRAPE_B200_NO_FORMSEG")) h->seg_fuse = false;
+        // real-symmetric generators, fused formation: prefix products by a parallel scan inside the formation kernel
+        // (one block of <= 128 segment threads per generator), no boundary chains (small_sym.cuh).  Without the chains
+        // short segments cost nothing extra, and the measured optimum of formation + contraction is at the shortest
+        // segments that keep the block full (profiles/r2_s1_c3_sweep.txt): NSEG ~ 128 for shards up to 2048
+        // trajectories, ~ 64 above.  GRAPE_B200_SEG_SCAN=0 keeps the chains.
+        h->seg_scan = h->seg_real && h->sym_v != 1 && h->seg_fuse && L <= 16 &&
+                      !(getenv("GRAPE_B200_SEG_SCAN") && atoi(getenv("GRAPE_B200_SEG_SCAN")) == 0);
+        if (h->seg_scan) {
+            const int target = K <= 2048 ? 128 : 64;
+            S = (NT + target - 1) / target;
+            if (S < 2) S = 2;
+        }
         if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
         a.S = S < 2 ? 2 : (S > 128 ? 128 : S);
         a.NSEG = (NT + a.S - 1) / a.S;
-        // enough (generator, segment) pairs to fill the GPU: one thread forms the propagators of its segment and their
-        // product; GRAPE_B200_NO_FORMSEG=1 / GRAPE_B200_FORCE_FORMSEG=1 override the size rule (tests)
-        h->seg_fuse = (long long)G * a.NSEG >= 32768;
-        if (getenv("GRAPE_B200_FORCE_FORMSEG") && atoi(getenv("GRAPE_B200_FORCE_FORMSEG")) != 0) h->seg_fuse = true;
-        if (getenv("GRAPE_B200_NO_FORMSEG")) h->seg_fuse = false;
+        if (h->seg_scan && a.NSEG > 32 * SCAN_MAXW) {   // a forced S too short for one block per generator
+            a.S = (NT + 32 * SCAN_MAXW - 1) / (32 * SCAN_MAXW);
+            a.NSEG = (NT + a.S - 1) / a.S;
+        }
         p.KB = (K + a.BKL - 1) / a.BKL;
         if (int rc = dev_alloc(h, &a.Pseg, (size_t)a.NSEG * NN * G)) return rc;
         if (int rc = dev_alloc(h, &a.chiE, (size_t)a.NSEG * N * K)) return rc;
@@ -363,16 +384,33 @@ void seg_formseg_t(H* h) {
     const long long tot = (long long)h->p.G * h->seg.NSEG;
     if (N <= 3 && h->seg_real) {
         constexpr int NS = N <= 3 ? N : 1;
-        cudaMemsetAsync(h->seg.notfast, 0, sizeof(int), h->stream);
         const unsigned blocks = (unsigned)((tot + SYM_BD - 1) / SYM_BD);
         const size_t sm = sym_stage_bytes(N, h->p.L);
-        if (h->sym_v == 1) small_formseg_sym<NS><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
-        else if (h->p.L == 1) small_formseg_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
+        if (h->seg_scan) {   // one block per generator, thread = segment, prefix products by a warp scan
+            const unsigned bd = 32u * (unsigned)((h->seg.NSEG + 31) / 32);
+            if (h->p.L == 1) small_formscan_sym<NS, 1><<<h->p.G, bd, 0, h->stream>>>(h->p, h->seg);
+            else if (h->p.L == 2) small_formscan_sym<NS, 2><<<h->p.G, bd, 0, h->stream>>>(h->p, h->seg);
+            else small_formscan_sym<NS, 0><<<h->p.G, bd, 0, h->stream>>>(h->p, h->seg);
+        } else if (h->sym_v == 1) {
+            cudaMemsetAsync(h->seg.notfast, 0, sizeof(int), h->stream);
+            small_formseg_sym<NS><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
+        } else if (h->p.L == 1) small_formseg_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
         else if (h->p.L == 2) small_formseg_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
         else small_formseg_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, h->seg);
     } else {
         small_formseg<N><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg);
     }
+    h->launches++;
+}
+template <int N>
+void seg_scan_tau_t(H* h) {
+    small_scan_tau_reduce<(N <= 3 ? N : 1)><<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p, h->seg);
+    h->launches++;
+}
+template <int N>
+void seg_scan_bounds_t(H* h, const cplx* chi_host, int fwd_only) {
+    const long long tot = (long long)h->p.K * h->seg.NSEG;
+    small_scan_bounds<(N <= 3 ? N : 1)><<<(unsigned)((tot + 127) / 128), 128, 0, h->stream>>>(h->p, h->seg, chi_host, fwd_only);
     h->launches++;
 }
 template <int N>
@@ -417,22 +455,28 @@ template <int N, int LCMAX>
 void seg_grad_t(H* h) {
     const int* run_if = nullptr;
     if (N <= 3 && seg_real_active(h)) {
-        // real-symmetric generators: all controls in one launch; if a step of this call is not eligible (flag written by
-        // small_formseg_sym) the kernel returns at once and the general Hermitian kernel below runs instead
+        // real-symmetric generators: all controls in one launch
         const SegArgs& a = h->seg;
         const int SPW = 32 / a.BKL;
         const long long warps = (long long)((h->p.K + a.BKL - 1) / a.BKL) * ((a.NSEG + SPW - 1) / SPW);
         constexpr int NS = N <= 3 ? N : 1;
         const unsigned blocks = (unsigned)((warps + 3) / 4);
         const size_t sm = sym_stage_bytes(N, h->p.L);
-        if (h->sym_v == 1) {   // round-1 kernels (operators re-loaded from global memory every step)
+        if (h->sym_v == 1) {
+            // round-1 kernels (operators re-loaded from global memory every step): if a step of this call is not eligible
+            // (flag written by small_formseg_sym) the kernel returns at once and the general Hermitian kernel below runs
             if (h->sym_occ == 2) small_seggrad_sym<NS, 2><<<blocks, 128, 0, h->stream>>>(h->p, a);
             else small_seggrad_sym<NS, 3><<<blocks, 128, 0, h->stream>>>(h->p, a);
-        } else if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
-        else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
-        else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
-        h->launches++;
-        run_if = a.notfast;
+            h->launches++;
+            run_if = a.notfast;
+        } else {
+            // staged kernels: every step is served (sub-stepping inside), no second launch
+            if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            h->launches++;
+            return;
+        }
     }
     if (h->seg_herm) seg_grad_launch<N, LCMAX, true>(h, run_if);
     else seg_grad_launch<N, LCMAX, false>(h, run_if);
@@ -464,6 +508,11 @@ void run_formU(H* h) {
 }
 void run_fill_interior(H* h) {
     if (h->path == GRAPE_B200_PATH_SMALL && h->seg_on && !h->interior_done) {
+        if (h->seg_scan && !h->bounds_done) {   // functional-only call: the boundary states were never needed so far
+            SMALL_DISPATCH(h->p.N, seg_scan_bounds_t<1>(h, nullptr, 1), seg_scan_bounds_t<2>(h, nullptr, 1),
+                           seg_scan_bounds_t<3>(h, nullptr, 1), seg_scan_bounds_t<3>(h, nullptr, 1));
+            h->bounds_done = true;
+        }
         if (!h->U_valid) {   // Hermitian schedule: the propagators were only accumulated into the segment products
             SMALL_DISPATCH(h->p.N, small_formU_t<1>(h), small_formU_t<2>(h), small_formU_t<3>(h), small_formU_t<4>(h));
             h->U_valid = true;
@@ -485,9 +534,15 @@ void run_xchg_begin(H* h, bool grad) {
     xchg_begin<<<1, 1, 0, h->stream>>>(h->xd, bump0, grad ? 1 : 0);
     h->launches++;
 }
-void run_forward(H* h, bool need_storage = true) {
+void run_forward(H* h, bool need_storage = true, bool with_backward = false) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
+            if (h->seg_on && h->seg_scan) {   // tau, final states and the sums straight from the prefix products
+                SMALL_DISPATCH(h->p.N, seg_scan_tau_t<1>(h), seg_scan_tau_t<2>(h), seg_scan_tau_t<3>(h), seg_scan_tau_t<3>(h));
+                h->interior_done = false;
+                h->bounds_done = false;
+                break;
+            }
             if (h->seg_on) {
                 SMALL_DISPATCH(h->p.N, seg_chain_fwd_t<1>(h), seg_chain_fwd_t<2>(h), seg_chain_fwd_t<3>(h), seg_chain_fwd_t<4>(h));
                 h->interior_done = false;
@@ -506,11 +561,13 @@ void run_forward(H* h, bool need_storage = true) {
         case GRAPE_B200_PATH_DENSE:
             kry_run_plan(h->dense, h->p, h->stream, h->launches);
             if (h->dense2.on) dense2_run_forward(h->dense2, h->dense, h->p, h->stream, h->launches);
-            else dense_run_forward(h->dense, h->p, h->stream, h->launches);
+            else dense_run_forward(h->dense, h->p, h->stream, h->launches, with_backward);
             break;
     }
-    reduce_tau<<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p);   // single block, fixed order; wider for large ensembles
-    h->launches++;
+    if (!(h->path == GRAPE_B200_PATH_SMALL && h->seg_on && h->seg_scan)) {   // (the scan schedule's tau kernel has done it)
+        reduce_tau<<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p);   // single block, fixed order; wider for large ensembles
+        h->launches++;
+    }
     // sharded over peers: chi of J_T_sm needs the global sum of tau before the backward sweep (optimize.jl:845-855);
     // a functional-only call needs the global sums for J itself. Otherwise the sums travel with the gradient.
     if (xchg_live(h) && (h->xchg_fonly || h->p.functional == GRAPE_B200_JT_SM)) {
@@ -521,6 +578,12 @@ void run_forward(H* h, bool need_storage = true) {
 void run_backward(H* h, const cplx* chi_host) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
+            if (h->seg_on && h->seg_scan) {
+                SMALL_DISPATCH(h->p.N, seg_scan_bounds_t<1>(h, chi_host, 0), seg_scan_bounds_t<2>(h, chi_host, 0),
+                               seg_scan_bounds_t<3>(h, chi_host, 0), seg_scan_bounds_t<3>(h, chi_host, 0));
+                h->bounds_done = true;
+                break;
+            }
             if (h->seg_on) {
                 if (!h->seg_herm) run_fill_interior(h);
                 SMALL_DISPATCH(h->p.N, seg_chain_bwd_t<1>(h, chi_host), seg_chain_bwd_t<2>(h, chi_host),
@@ -554,7 +617,7 @@ void run_gradient(H* h) {
             break;
         case GRAPE_B200_PATH_WARP: warp_run_gradient(h->warp, h->p, h->stream, h->launches); break;
         case GRAPE_B200_PATH_DENSE:   // block recursion: fused into the backward sweep; Krylov form: contraction over all steps
-            kry_run_gradient(h->dense, h->p, h->stream, h->launches);
+            kry_run_gradient(h->dense, h->p, h->stream, h->launches, h->dense.dual_launched);
             break;
     }
 }
@@ -656,7 +719,7 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
         cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream);
         run_xchg_begin(h, grad);
         run_formU(h);
-        run_forward(h, grad);
+        run_forward(h, grad, grad);
         if (grad) { run_backward(h, nullptr); run_gradient(h); }
         run_finalize(h, grad);
         cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * h->out_doubles, cudaMemcpyDeviceToHost, h->stream);
@@ -672,6 +735,7 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
     h->launches += gl;
     // the captured sequence of eval_f leaves the interior of fw_storage unfilled
     if (h->seg_on || h->wseg_on) h->interior_done = grad && !h->seg_herm;
+    if (h->seg_scan) h->bounds_done = grad;
     if (h->path == GRAPE_B200_PATH_SMALL)   // same bookkeeping as run_formU (not executed on a graph replay)
         h->U_valid = !(seg_fused(h) && !h->seg.store_U);
     return 1;
@@ -696,7 +760,7 @@ int eval_launch(H* h, const double* pulsevals, bool grad) {
         if (int rc = upload_pulses(h, pulsevals)) return rc;
         run_xchg_begin(h, grad);
         run_formU(h); rec(h, 1);
-        run_forward(h, grad); rec(h, 2);   // functional only: the interior of fw_storage is filled lazily (get_stored_states)
+        run_forward(h, grad, grad); rec(h, 2);   // functional only: the interior of fw_storage is filled lazily (get_stored_states)
         rec(h, 3);
         if (grad) { run_backward(h, nullptr); rec(h, 4); run_gradient(h); }
         else rec(h, 4);
@@ -780,7 +844,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->taugrads_valid = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
-    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->d_taugrads = nullptr; h->taugrads_valid = false;
+    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->seg_scan = false; h->bounds_done = false; h->d_taugrads = nullptr; h->taugrads_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     memset(&h->xd, 0, sizeof h->xd); h->xchg_on = false; h->xchg_mode = false; h->xchg_fonly = false;
     h->xchg_buf = nullptr; h->xchg_bytes = 0; h->launched_via_graph = false; h->launch_l0 = 0;
@@ -868,6 +932,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
             if (!rc && !h->dense2.on && !h->dense.strip_ok) { e = h->dense.strip_err; rc = GRAPE_B200_EINVAL; }
             if (!rc) rc = kry_setup(h->dense, h->dense2, p, h->dev_allocs, e);
             if (!rc) rc = dense_dual_setup(h->dense, p, h->dense2.on, h->dev_allocs, e);
+            if (!rc) rc = dense_concurrent_setup(h->dense, p, d->tgt, h->dense2.on, h->dev_allocs, e);
             if (!rc) rc = dense2_multi_setup(h->dense2, h->dense, e);
             if (rc) h->err = e;
             break;
@@ -995,7 +1060,7 @@ int grape_b200_enqueue_forward(grape_b200_handle* h, const double* d_pulsevals) 
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
     run_xchg_begin(h, true);
     run_formU(h); rec(h, 1);
-    run_forward(h); rec(h, 2); rec(h, 3);
+    run_forward(h, true, h->p.functional != GRAPE_B200_JT_HOST); rec(h, 2); rec(h, 3);   // enqueue_backward follows
     h->forward_done = true; h->backward_done = false; h->taugrads_valid = false;
     return 0;
 }
@@ -1044,7 +1109,7 @@ int grape_b200_eval_fg_device(grape_b200_handle* h, const double* d_pulsevals, d
     CUDA_TRY(h, cudaMemsetAsync(h->p.flags, 0, sizeof(DevFlags), h->stream));
     run_xchg_begin(h, true);
     run_formU(h); rec(h, 1);
-    run_forward(h); rec(h, 2); rec(h, 3);
+    run_forward(h, true, true); rec(h, 2); rec(h, 3);
     run_backward(h, nullptr); rec(h, 4);
     run_gradient(h);
     run_finalize(h, true); rec(h, 5);
@@ -1194,11 +1259,24 @@ int grape_b200_gradient_form(grape_b200_handle* h) {
     return ok ? (h->dense.d.nstrip > 1 ? 2 : 1) : 0;
 }
 
+int grape_b200_dense_concurrent(grape_b200_handle* h) {
+    if (!h) return -GRAPE_B200_EINVAL;
+    if (h->path != GRAPE_B200_PATH_DENSE || !h->dense.concurrent || !h->dense.dual_launched) return 0;
+    int ok = 0;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
+        cudaMemcpy(&ok, h->dense.kd.ok, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        h->err = "CUDA error while reading the gradient form";
+        return -GRAPE_B200_ECUDA;
+    }
+    return ok ? 1 : 0;
+}
+
 int grape_b200_small_schedule(grape_b200_handle* h) {
     if (!h) return -GRAPE_B200_EINVAL;
     if (h->path != GRAPE_B200_PATH_SMALL || !h->seg_on) return 0;
     if (!h->seg_herm) return 1;
     if (!seg_real_active(h)) return 2;
+    if (h->sym_v != 1) return 3;   // the staged kernels serve every step themselves
     int nf = 0;
     if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
         cudaMemcpy(&nf, h->seg.notfast, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {

@@ -54,6 +54,9 @@ struct KryDev {
     double* kcur;      // [2][Np][Kp]  state of the backward chain
     double* kcur2;     // ping-pong partner (tiled chain)
     double* tilepart;  // [NT][TT][L]
+    int conc;          // concurrent forward / backward chains (dense_chain<2, NS>): the chi chain propagates tgt_k / ||tgt_k||
+    double* kfac;      // [2][Kp] (re, im) ||tgt_k|| conj(c_k): factor of e_b in kry_combine instead of rho_k
+    const double* tgtn;// [2][Np][Kp] planar tgt_k / ||tgt_k||: start of the concurrent chi chain
 };
 
 struct DenseDev {
@@ -94,9 +97,14 @@ struct DensePlan {
     size_t smemF, smemB;
     size_t smemF2;        // dense_chain<BWD, NS >= 2>: further operator strips
     bool ready;
+    bool concurrent;      // dense_chain<2, NS> available for this handle (no state running cost, built-in chi, 2 RT <= SMs)
+    bool dual_launched;   // the forward phase of the current call enqueued the concurrent chains
+    DenseDev dD;          // copy of d with the column split of the concurrent launch (Pf, CcapF)
+    int gridD;
+    size_t smemD;
     bool strip_ok;        // the 8-row strip kernels of this file can run (N, K(L+1) small enough)
     std::string strip_err;
-    DensePlan() : kry_smem(0), gridF(0), gridB(0), smemF(0), smemB(0), smemF2(0), ready(false), strip_ok(true) { memset(&kd, 0, sizeof kd); }
+    DensePlan() : kry_smem(0), gridF(0), gridB(0), smemF(0), smemB(0), smemF2(0), ready(false), concurrent(false), dual_launched(false), gridD(0), smemD(0), strip_ok(true) { memset(&kd, 0, sizeof kd); memset(&dD, 0, sizeof dD); }
 };
 
 GB_D void dmma884(double (&acc)[2], double a, double b) {
@@ -477,12 +485,25 @@ GB_D void dense_prefetch_strips(const double* __restrict__ pre, int n, int Np, i
 // computed from the same operand fragments: ceil(m/NS) instead of m dependent stages per step.  With the pre-formed
 // generators (DenseDev::preF / preA; required for NS = 3) the strips of step n+1 are fetched by cp.async behind the
 // last stage of step n.
-template <bool BWD, int NS>
-__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev d, KryDev kd) {
-    if (BWD && !(*kd.ok)) return;   // uniform over the grid
+// MODE 0: forward sweep, MODE 1: chi chain, MODE 2: BOTH AT ONCE -- the first half of the grid runs the forward sweep
+// upwards in n while the second half runs the chi chain downwards from n = NT - 1, sharing the grid barriers.  That is
+// possible because chi_k(T) of J_T_sm / J_T_re / J_T_ss is c_k tgt_k with a SCALAR c_k that depends on the forward
+// result (optimize.jl:845-855, docs/src/tutorial.md:399-405) and the backward propagation is linear: the chain
+// propagates tgt_k / ||tgt_k||, and the factor ||tgt_k|| conj(c_k) (= rho_k times the phase of c_k) goes into the
+// combination e_b of the contraction (kry_combine) once the forward sweep has produced tau.  Not applicable with a
+// state running cost (its inhomogeneity needs Psi(t_{n-1}) while chi is propagated, optimize.jl:897-908) nor with
+// a host chi.  A 2 N_T m / NS-stage latency chain becomes N_T m / NS stages of twice the width.
+// skip_if_ok: return at once when the call qualifies for the Krylov form (MODE 2 has done / will do this sweep).
+template <int MODE, int NS>
+__global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev d, KryDev kd, int skip_if_ok) {
+    if (MODE >= 1 && !(*kd.ok)) return;   // uniform over the grid
+    if (skip_if_ok && *kd.ok) return;
     extern __shared__ __align__(16) double dsm[];
     const int Np = d.Np, Kp = d.Kp, MS = d.MS, NT = p.NT;
-    const int rt = blockIdx.x / d.Pf, part = blockIdx.x % d.Pf;
+    const int half = MODE == 2 ? (int)(gridDim.x / 2) : 0;
+    const bool BWD = MODE == 1 || (MODE == 2 && (int)blockIdx.x >= half);
+    const int bid = (MODE == 2 && BWD) ? (int)blockIdx.x - half : (int)blockIdx.x;
+    const int rt = bid / d.Pf, part = bid % d.Pf;
     // One cooperative_groups grid barrier per Taylor term: ncu attributes ~40 % of this kernel to it (arrival skew
     // after every CTA pulls its whole operand block from L2 at the same instant + the barrier round trips).  Two
     // replacements were measured on C4 and were SLOWER (profiles/r1_s5_*, r1_s7_*): a two-level counter barrier
@@ -502,6 +523,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
     double* coef = jb_s + Ccap + 8;                 // NS >= 2: pair coefficients c_i c_j of the current step (<= 64)
     double* HX = coef + 64;                         // NS >= 2: rows of H_n^2 [, H_n^3], 16 MS doubles each
     constexpr bool DUAL = NS >= 2;
+    auto stages_of = [&](int mm) { return DUAL ? (mm + NS - 1) / NS : mm; };   // grid barriers of a Krylov-form step
     const double* const Bq[3] = {Hs_re, HX, HX + 16 * MS};
     const size_t splane = (size_t)Np * Kp;
     const int w = threadIdx.x >> 5;
@@ -571,7 +593,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
         else dense_form_H(p, Hall, Np, MS, r0, n, Hs_re, Hs_im);
         int m, s;
         dense_plan(p, d, n, dt, m, s);
-        if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
+        if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && bid == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
         const bool kry = kd.on && s == 0 && m <= kd.MT;
         double* slots = kry ? terms + (size_t)n * kd.MT * 2 * splane : nullptr;
@@ -614,10 +636,11 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                         else if (q == 1) { tr = -x * r.x; ti = -x * r.y; }
                         else { tr = BWD ? x * r.y : -x * r.y; ti = BWD ? -x * r.x : x * r.x; }
                     };
-                    for (int pg = cg0; pg < cg1; pg += DENSE_CGP) {
-                        const int ng = min(DENSE_CGP, cg1 - pg);
+                    const int pgstep = nt == NS ? 1 : DENSE_CGP;   // full stage: one 8-column group per pass, all NS strips
+                    for (int pg = cg0; pg < cg1; pg += pgstep) {
+                        const int ng = min(pgstep, cg1 - pg);
                         const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
-                        if (ng == 1 && nt == NS) {
+                        if (nt == NS) {
                             DAcc acc[NS];
 #pragma unroll
                             for (int q = 0; q < NS; ++q) acc[q].zero();
@@ -759,11 +782,15 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
             }
             grid.sync();
         }
+        if (MODE == 2) {   // both directions make the same number of grid barriers per iteration (uniform per role)
+            const int mo = kd.m_n[BWD ? it : NT - 1 - it];
+            for (int x = stages_of(m); x < stages_of(mo); ++x) grid.sync();
+        }
     }
     if (!BWD && gb) {
         gb_point(0.5 * (p.tlist[NT] - p.tlist[NT - 1]));
         for (int c = threadIdx.x; c < ncols; c += DENSE_THREADS)
-            d.jbpart[(size_t)blockIdx.x * Kp + cbeg + c] = jb_s[c];
+            d.jbpart[(size_t)bid * Kp + cbeg + c] = jb_s[c];
     }
 }
 
@@ -955,7 +982,8 @@ __global__ void __launch_bounds__(256) dense_tau(DevP p, DenseDev d, int gridF) 
 }
 
 // chi_k(T) boundary condition, normalisation, initial backward block  (optimize.jl:845-869, 878)
-__global__ void __launch_bounds__(256) dense_boundary(DevP p, DenseDev d, const cplx* __restrict__ chi_host, double* __restrict__ kcur) {
+__global__ void __launch_bounds__(256) dense_boundary(DevP p, DenseDev d, const cplx* __restrict__ chi_host, double* __restrict__ kcur,
+                                                      double* __restrict__ kfac) {
     __shared__ double s_buf[32];
     __shared__ double s_rho;
     const int k = blockIdx.x;
@@ -1003,6 +1031,11 @@ __global__ void __launch_bounds__(256) dense_boundary(DevP p, DenseDev d, const 
         }
         p.rho[k] = rho;
         s_rho = rho;
+        if (kfac) {   // concurrent chains: chi_k = (c_k / |c_k|) x (propagated tgt_k / ||tgt_k||), rho_k = |c_k| ||tgt_k||
+            const double ac = sqrt(c.x * c.x + c.y * c.y);
+            kfac[k] = ac > 0.0 ? rho * c.x / ac : 0.0;
+            kfac[d.Kp + k] = ac > 0.0 ? -rho * c.y / ac : 0.0;
+        }
     }
     __syncthreads();
     const double ir = 1.0 / s_rho;
@@ -1188,8 +1221,8 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     }
     if (dp.smemF > 227 * 1024 || dp.smemB > 227 * 1024) { dp.strip_ok = false; dp.strip_err = "dense strip kernels: shared-memory tile does not fit (N or K*(L+1) too large)"; }
     if (dp.strip_ok) {
-        cudaError_t e = cudaFuncSetAttribute(dense_chain<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_chain<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        cudaError_t e = cudaFuncSetAttribute(dense_chain<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_chain<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemF);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dense_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dp.smemB);
         if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e); return GRAPE_B200_ECUDA; }
     }
@@ -1319,14 +1352,73 @@ inline int dense_dual_setup(DensePlan& dp, const DevP& p, bool tiled_chains, std
         return 0;
     }
     const size_t smem = smem_of(ns);
-    cudaError_t e = ns == 3 ? cudaFuncSetAttribute(dense_chain<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                            : cudaFuncSetAttribute(dense_chain<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ns == 3 ? cudaFuncSetAttribute(dense_chain<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                            : cudaFuncSetAttribute(dense_chain<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
-        e = ns == 3 ? cudaFuncSetAttribute(dense_chain<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                    : cudaFuncSetAttribute(dense_chain<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = ns == 3 ? cudaFuncSetAttribute(dense_chain<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : cudaFuncSetAttribute(dense_chain<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); d.preF = d.preA = nullptr; return 0; }
     d.PPf = pf; d.PPa = pa; d.nP = nP; d.PTf = tf; d.PTa = ta; d.nP3 = nP3; d.nstrip = ns;
     dp.smemF2 = smem;
+    return 0;
+}
+
+// Concurrent forward / backward chains (dense_chain<2, NS>): 2 x RT x Pf2 CTAs in one cooperative grid.
+// Needs the Krylov form (term stores), a built-in functional (chi_k = c_k tgt_k), no state running cost, the strip
+// kernels, and room for both directions on the device.  GRAPE_B200_DENSE_CONCURRENT=0 disables.  Called after
+// dense_dual_setup; `tgt_host` = the ABI's [K][N] complex target states.
+inline int dense_concurrent_setup(DensePlan& dp, const DevP& p, const double* tgt_host, bool tiled_chains,
+                                  std::vector<void*>& allocs, std::string& err) {
+    DenseDev& d = dp.d;
+    dp.concurrent = false;
+    dp.kd.conc = 0;
+    if (const char* env = getenv("GRAPE_B200_DENSE_CONCURRENT")) { if (atoi(env) == 0) return 0; }
+    if (!dp.kd.on || tiled_chains || !dp.strip_ok || p.gb_kind != 0 || p.functional == GRAPE_B200_JT_HOST) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (2 * d.RT > sms) return 0;
+    DenseDev dd = d;
+    dd.Pf = std::max(1, std::min(std::max(1, sms / (2 * d.RT)), d.Kp / 8));
+    dd.CcapF = ((d.Kp / 8 + dd.Pf - 1) / dd.Pf) * 8;
+    const size_t redB = (size_t)(DENSE_THREADS / 32) * DENSE_CGP * 128;
+    size_t smem = sizeof(double) * (16 * (size_t)d.MS + 16 * (size_t)dd.CcapF + redB + dd.CcapF + 8);
+    if (d.nstrip >= 2) smem += sizeof(double) * (64 + (size_t)(d.nstrip - 1) * 16 * d.MS);
+    if (smem > 227 * 1024) return 0;
+    cudaError_t e = d.nstrip == 3 ? cudaFuncSetAttribute(dense_chain<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : d.nstrip == 2 ? cudaFuncSetAttribute(dense_chain<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(dense_chain<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    // normalised targets (static) and the per-call factors
+    const size_t splane = (size_t)d.Np * d.Kp;
+    std::vector<double> tn(2 * splane, 0.0);
+    for (int k = 0; k < p.K; ++k) {
+        double nn = 0.0;
+        for (int i = 0; i < p.N; ++i) {
+            const double re = tgt_host[2 * ((size_t)k * p.N + i)], im = tgt_host[2 * ((size_t)k * p.N + i) + 1];
+            nn += re * re + im * im;
+        }
+        nn = std::sqrt(nn);
+        if (!(nn > 0.0)) return 0;   // a trajectory without target state: chi_k(T) = 0, the sequential path reports it
+        for (int i = 0; i < p.N; ++i) {
+            tn[(size_t)i * d.Kp + k] = tgt_host[2 * ((size_t)k * p.N + i)] / nn;
+            tn[splane + (size_t)i * d.Kp + k] = tgt_host[2 * ((size_t)k * p.N + i) + 1] / nn;
+        }
+    }
+    void* q = nullptr;
+    if (cudaMalloc(&q, tn.size() * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    allocs.push_back(q);
+    if (cudaMemcpy(q, tn.data(), tn.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) { err = "cudaMemcpy failed"; return GRAPE_B200_ECUDA; }
+    dp.kd.tgtn = static_cast<const double*>(q);
+    if (cudaMalloc(&q, 2 * (size_t)d.Kp * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    allocs.push_back(q);
+    cudaMemset(q, 0, 2 * (size_t)d.Kp * sizeof(double));
+    dp.kd.kfac = static_cast<double*>(q);
+    dp.dD = dd;
+    dp.gridD = 2 * d.RT * dd.Pf;
+    dp.smemD = smem;
+    dp.kd.conc = 1;
+    dp.concurrent = true;
     return 0;
 }
 
@@ -1348,39 +1440,56 @@ inline void dense_run_preform(DensePlan& dp, const DevP& p, bool adjoint, cudaSt
     else dense_preform_launch<3>(d, p, adjoint, grid, chunk, st);
     launches++;
 }
-template <bool BWD>
+template <int MODE>
 inline void dense_chain_launch(DensePlan& dp, void** args, cudaStream_t st) {
     const DenseDev& d = dp.d;
-    if (d.nstrip == 3) cudaLaunchCooperativeKernel((void*)dense_chain<BWD, 3>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF2, st);
-    else if (d.nstrip == 2) cudaLaunchCooperativeKernel((void*)dense_chain<BWD, 2>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF2, st);
-    else cudaLaunchCooperativeKernel((void*)dense_chain<BWD, 1>, dim3(dp.gridF), dim3(DENSE_THREADS), args, dp.smemF, st);
+    const int grid = MODE == 2 ? dp.gridD : dp.gridF;
+    const size_t sm1 = MODE == 2 ? dp.smemD : dp.smemF, sm2 = MODE == 2 ? dp.smemD : dp.smemF2;
+    if (d.nstrip == 3) cudaLaunchCooperativeKernel((void*)dense_chain<MODE, 3>, dim3(grid), dim3(DENSE_THREADS), args, sm2, st);
+    else if (d.nstrip == 2) cudaLaunchCooperativeKernel((void*)dense_chain<MODE, 2>, dim3(grid), dim3(DENSE_THREADS), args, sm2, st);
+    else cudaLaunchCooperativeKernel((void*)dense_chain<MODE, 1>, dim3(grid), dim3(DENSE_THREADS), args, sm1, st);
 }
 
-inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int64_t& launches) {
+inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int64_t& launches, bool with_backward = false) {
     DenseDev& d = dp.d;
     const size_t splane = (size_t)d.Np * d.Kp;
     cudaMemcpyAsync(d.cur, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(d.store, d.psi0, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
     DevP pp = p;
-    void* args[] = {&pp, &d, &dp.kd};
+    int skip = 0;
     if (d.nstrip > 1 && d.preF) dense_run_preform(dp, p, false, st, launches);
-    dense_chain_launch<false>(dp, args, st);
+    dp.dual_launched = dp.concurrent && with_backward;
+    if (dp.dual_launched) {
+        // a gradient evaluation: both chains at once (the kernel returns at once unless the call qualifies for the
+        // Krylov form; then the forward-only kernel below does the sweep as before)
+        if (d.nstrip > 1 && d.preA && d.preA != d.preF) dense_run_preform(dp, p, true, st, launches);
+        cudaMemcpyAsync(dp.kd.kcur, dp.kd.tgtn, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        void* dargs[] = {&pp, &dp.dD, &dp.kd, &skip};
+        dense_chain_launch<2>(dp, dargs, st);
+        launches++;
+        skip = 1;
+    }
+    void* args[] = {&pp, &d, &dp.kd, &skip};
+    dense_chain_launch<0>(dp, args, st);
     dense_tau<<<p.K, 256, 0, st>>>(p, d, dp.gridF);
     launches += 2;
 }
 inline void dense_run_backward(DensePlan& dp, const DevP& p, const cplx* chi_host, cudaStream_t st, int64_t& launches) {
     DenseDev& d = dp.d;
     const size_t bplane = (size_t)d.Np * d.Cb;
+    const bool dual = dp.dual_launched && !chi_host;
     cudaMemsetAsync(d.bcur, 0, 2 * bplane * sizeof(double), st);
-    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host, dp.kd.on ? dp.kd.kcur : nullptr);
+    // after concurrent chains kcur holds the propagated chi: the boundary kernel must not overwrite the term stores' input
+    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host, (dp.kd.on && !dual) ? dp.kd.kcur : nullptr, dual ? dp.kd.kfac : nullptr);
     DevP pp = p;
     void* args[] = {&pp, &d};
     cudaLaunchCooperativeKernel((void*)dense_backward, dim3(dp.gridB), dim3(DENSE_THREADS), args, dp.smemB, st);
     launches += 2;
     if (dp.kd.on) {
-        void* cargs[] = {&pp, &d, &dp.kd};
-        if (d.nstrip > 1 && d.preA && d.preA != d.preF) dense_run_preform(dp, p, true, st, launches);
-        dense_chain_launch<true>(dp, cargs, st);
+        int skip = dual ? 1 : 0;
+        void* cargs[] = {&pp, &d, &dp.kd, &skip};
+        if (!dual && d.nstrip > 1 && d.preA && d.preA != d.preF) dense_run_preform(dp, p, true, st, launches);
+        dense_chain_launch<1>(dp, cargs, st);
         launches += 1;
     }
 }

@@ -672,7 +672,7 @@ inline void dense2_run_backward(Dense2Plan& q, DensePlan& dp, const DevP& p, con
     DenseDev& d = dp.d;
     const size_t bplane = (size_t)d.Np * d.Cb;
     cudaMemsetAsync(d.bcur, 0, 2 * bplane * sizeof(double), st);
-    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host, dp.kd.on ? dp.kd.kcur : nullptr);
+    dense_boundary<<<p.K, 256, 0, st>>>(p, d, chi_host, dp.kd.on ? dp.kd.kcur : nullptr, nullptr);
     DevP pp = p;
     void* args[] = {&pp, &d, &q.d2};
     void* fn = nullptr;

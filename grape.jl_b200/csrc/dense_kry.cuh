@@ -59,30 +59,63 @@ __global__ void __launch_bounds__(256) kry_plan(DevP p, DenseDev d, KryDev kd) {
     }
 }
 
-// e_b = rho_k sum_{a=0}^{m-1-b} beta(a,b) bh_a, in place in the forward term slots (bh_0 = fw_storage[n])
-__global__ void __launch_bounds__(256) kry_combine(DevP p, DenseDev d, KryDev kd) {
+// e_b = rho_k sum_{a=0}^{m-1-b} beta(a,b) bh_a, in place in the forward term slots (bh_0 = fw_storage[n]).
+// Concurrent chains (kd.conc, dense_chain<2, NS>): the chi chain carried tgt_k / ||tgt_k||, and the complex factor
+// f_k = ||tgt_k|| conj(c_k) replaces rho_k (M_n = sum e_b ch_b^dagger is anti-linear in chi).
+__global__ void __launch_bounds__(256) kry_combine(DevP p, DenseDev d, KryDev kd, int conc) {
     if (!(*kd.ok)) return;
-    const size_t slot = 2 * (size_t)d.Np * d.Kp;
-    const size_t total = (size_t)p.NT * slot;
+    const size_t splane = (size_t)d.Np * d.Kp, slot = 2 * splane;
+    if (!conc) {
+        const size_t total = (size_t)p.NT * slot;
+        for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+            const int n = (int)(e / slot);
+            const size_t r = e % slot;
+            const int k = (int)(r % d.Kp);
+            const int m = kd.m_n[n];
+            const double rho = k < p.K ? p.rho[k] : 0.0;
+            double* ft = kd.FT + (size_t)n * kd.MT * slot + r;
+            double v[KRY_MTMAX];
+            v[0] = __ldcs(&d.store[(size_t)n * slot + r]);
+#pragma unroll
+            for (int a = 1; a < KRY_MTMAX; ++a) v[a] = a < m ? __ldcs(&ft[(size_t)a * slot]) : 0.0;
+#pragma unroll
+            for (int b = 0; b < KRY_MTMAX; ++b) {
+                if (b < m) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int a = 0; a < KRY_MTMAX - b; ++a)
+                        if (a < m - b) s = fma(c_kbeta.v[a][b], v[a], s);
+                    ft[(size_t)b * slot] = rho * s;
+                }
+            }
+        }
+        return;
+    }
+    const size_t total = (size_t)p.NT * splane;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int n = (int)(e / slot);
-        const size_t r = e % slot;
+        const int n = (int)(e / splane);
+        const size_t r = e % splane;
         const int k = (int)(r % d.Kp);
         const int m = kd.m_n[n];
-        const double rho = k < p.K ? p.rho[k] : 0.0;
+        const double fr = k < p.K ? kd.kfac[k] : 0.0, fi = k < p.K ? kd.kfac[d.Kp + k] : 0.0;
         double* ft = kd.FT + (size_t)n * kd.MT * slot + r;
-        double v[KRY_MTMAX];
-        v[0] = __ldcs(&d.store[(size_t)n * slot + r]);
+        double vr[KRY_MTMAX], vi[KRY_MTMAX];
+        vr[0] = __ldcs(&d.store[(size_t)n * slot + r]);
+        vi[0] = __ldcs(&d.store[(size_t)n * slot + splane + r]);
 #pragma unroll
-        for (int a = 1; a < KRY_MTMAX; ++a) v[a] = a < m ? __ldcs(&ft[(size_t)a * slot]) : 0.0;
+        for (int a = 1; a < KRY_MTMAX; ++a) {
+            vr[a] = a < m ? __ldcs(&ft[(size_t)a * slot]) : 0.0;
+            vi[a] = a < m ? __ldcs(&ft[(size_t)a * slot + splane]) : 0.0;
+        }
 #pragma unroll
         for (int b = 0; b < KRY_MTMAX; ++b) {
             if (b < m) {
-                double s = 0.0;
+                double sr = 0.0, si = 0.0;
 #pragma unroll
                 for (int a = 0; a < KRY_MTMAX - b; ++a)
-                    if (a < m - b) s = fma(c_kbeta.v[a][b], v[a], s);
-                ft[(size_t)b * slot] = rho * s;
+                    if (a < m - b) { sr = fma(c_kbeta.v[a][b], vr[a], sr); si = fma(c_kbeta.v[a][b], vi[a], si); }
+                ft[(size_t)b * slot] = fr * sr - fi * si;
+                ft[(size_t)b * slot + splane] = fr * si + fi * sr;
             }
         }
     }
@@ -292,12 +325,12 @@ inline void kry_run_plan(DensePlan& dp, const DevP& p, cudaStream_t st, int64_t&
 }
 
 // after the backward chain: combine, contract, reduce (each returns at once if the call took the block recursion)
-inline void kry_run_gradient(DensePlan& dp, const DevP& p, cudaStream_t st, int64_t& launches) {
+inline void kry_run_gradient(DensePlan& dp, const DevP& p, cudaStream_t st, int64_t& launches, bool conc = false) {
     if (!dp.kd.on) return;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    kry_combine<<<sms * 8, 256, 0, st>>>(p, dp.d, dp.kd);
+    kry_combine<<<sms * 8, 256, 0, st>>>(p, dp.d, dp.kd, conc ? 1 : 0);
     const long long total = (long long)p.NT * dp.kd.TT;
     const int grid = (int)std::min<long long>(total, sms);
     if (dp.kd.KC == 16) kry_contract<16><<<grid, KM_THREADS, dp.kry_smem, st>>>(p, dp.d, dp.kd);

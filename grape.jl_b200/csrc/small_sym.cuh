@@ -434,7 +434,6 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_formseg_sym2(DevP p, SegArgs 
         const double dt = p.tlist[n + 1] - p.tlist[n];
         double Hs[NN];
         const double theta = dt * sym_form_H_staged<N, LT>(p, sH, L, n, Hs);
-        if (theta > c_sym_th[SEG_MMAX]) *a.notfast = 1;   // the gradient kernel of this file cannot serve this step
         double Cm[NN], Sm[NN];
         sym_cos_sin<N>(Hs, dt, theta, Cm, Sm);
         if (n == n0) {
@@ -466,11 +465,25 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_formseg_sym2(DevP p, SegArgs 
     for (int c = 0; c < NN; ++c) o[(size_t)c * G] = mk(Pr[c], Pi[c]);
 }
 
+// rare steps beyond 8 orders: nsub equal sub-steps (kept out of line so that the hot path's registers are not affected)
+template <int N>
+__device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], cplx (&chi)[N], double (&IM)[N * N], int nsub) {
+    constexpr int NN = N * N;
+    const double f = 1.0 / (double)nsub;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) { Hs[c] *= f; IM[c] = 0.0; }
+    for (int sub = 0; sub < nsub; ++sub) {
+        double IS[NN];
+        sym_step<N, 8>(Hs, psi, chi, IS);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) IM[c] = fma(f, IS[c], IM[c]);
+    }
+}
+
 template <int N, int LT>
 __global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
-    if (*a.notfast) return;   // uniform over the grid: small_seggrad<N, LC, true> serves this call
     const int K = p.K, NT = p.NT, L = LT > 0 ? LT : p.L;
     const int lane = threadIdx.x & 31;
     const int BKL = a.BKL, SPW = 32 / BKL;
@@ -506,18 +519,37 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs 
         int m = 2;
 #pragma unroll
         for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;
+        // steps beyond 8 orders (||H dt||_1 > 0.0308): nsub equal sub-steps of 8 orders each -- the integral
+        // M = int_0^1 Psi(s) chi(s)^dagger ds of the step is the mean of the sub-steps' integrals.  Decided per warp and
+        // per step (round 1 sent the WHOLE call to the 1.8x slower complex kernel if one step anywhere was ineligible).
+        int nsub = theta > c_sym_th[SEG_MMAX] ? (int)ceil(theta / c_sym_th[SEG_MMAX]) : 1;
         m = __reduce_max_sync(0xffffffffu, m);   // more orders never hurt: one uniform branch per warp
+        nsub = __reduce_max_sync(0xffffffffu, nsub);
 #pragma unroll
         for (int c = 0; c < NN; ++c) Hs[c] *= dt;
         double IM[NN];
-        switch (m) {
-            case 2: sym_step<N, 2>(Hs, psi, chi, IM); break;
-            case 3: sym_step<N, 3>(Hs, psi, chi, IM); break;
-            case 4: sym_step<N, 4>(Hs, psi, chi, IM); break;
-            case 5: sym_step<N, 5>(Hs, psi, chi, IM); break;
-            case 6: sym_step<N, 6>(Hs, psi, chi, IM); break;
-            case 7: sym_step<N, 7>(Hs, psi, chi, IM); break;
-            default: sym_step<N, 8>(Hs, psi, chi, IM); break;
+        if (nsub == 1) {
+            switch (m) {
+                case 2: sym_step<N, 2>(Hs, psi, chi, IM); break;
+                case 3: sym_step<N, 3>(Hs, psi, chi, IM); break;
+                case 4: sym_step<N, 4>(Hs, psi, chi, IM); break;
+                case 5: sym_step<N, 5>(Hs, psi, chi, IM); break;
+                case 6: sym_step<N, 6>(Hs, psi, chi, IM); break;
+                case 7: sym_step<N, 7>(Hs, psi, chi, IM); break;
+                default: sym_step<N, 8>(Hs, psi, chi, IM); break;
+            }
+        } else {   // copies: only they live in local memory for the out-of-line call
+            double Hs2[NN], IM2[NN];
+            cplx psi2[N], chi2[N];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Hs2[c] = Hs[c];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { psi2[i] = psi[i]; chi2[i] = chi[i]; }
+            sym_step_sub<N>(Hs2, psi2, chi2, IM2, nsub);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) IM[c] = IM2[c];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { psi[i] = psi2[i]; chi[i] = chi2[i]; }
         }
         auto one_control = [&](int l) {
             double sl = dt * rho;
@@ -537,4 +569,269 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs 
             for (int l = 0; l < L; ++l) one_control(l);
         }
     }
+}
+
+// ===========================================================================================
+// Round 2: no sequential chains at all -- the segment propagators are combined by a PARALLEL SCAN.
+//
+// B1 / B2 (small_segchain_fwd / _bwd) walk the NSEG segment boundaries one after the other: 18 + 13 us of pure
+// dependency latency per gradient at K = 4096 and 23 + 21 us of a 130 us step at K = 512 (a shard of the ensemble
+// on 8 GPUs; profiles/r2_s1_c3_sweep.txt).  Matrix products are associative, so the prefix products
+//     Q_seg = P_seg P_{seg-1} ... P_0
+// come from a Kogge-Stone scan across the lanes of the warp that formed the P_seg of one generator (5 levels of
+// 3 x 3 complex products exchanged by shuffles, +4 % work in the formation kernel), and with them every boundary
+// state is ONE mat-vec, independent of all the others:
+//     Psi_k(end of seg) = Q_seg Psi_k(0),      tau_k = <tgt_k | Q_last Psi_k(0)>,
+//     chi_k(end of seg) = (P_last .. P_{seg+1})^dagger chi_k(T) = Q_seg Q_last^dagger chi_k(T)   (Hermitian generators:
+//     every P is unitary).
+//   A2'' small_formscan_sym      one block per generator, thread = segment: P_seg as in A2', then the scan
+//   B'   small_scan_tau_reduce   tau_k, final states and the sums of reduce_tau (single block, fixed order)
+//   B''  small_scan_bounds       thread per (k, seg): chi_k(T) (optimize.jl:845-869), Psi / chi at the segment ends
+// The gradient kernel C2' is unchanged (it reads the same boundary arrays the chains used to fill).
+// ===========================================================================================
+
+// C = A B, complex N x N on split real / imaginary arrays
+template <int N>
+GB_D void cm_mm(double (&Cr)[N * N], double (&Ci)[N * N], const double (&Ar)[N * N], const double (&Ai)[N * N],
+                const double (&Br)[N * N], const double (&Bi)[N * N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                ar = fma(Ar[i * N + k], Br[k * N + j], ar);
+                ar = fma(-Ai[i * N + k], Bi[k * N + j], ar);
+                ai = fma(Ar[i * N + k], Bi[k * N + j], ai);
+                ai = fma(Ai[i * N + k], Br[k * N + j], ai);
+            }
+            Cr[i * N + j] = ar;
+            Ci[i * N + j] = ai;
+        }
+}
+
+constexpr int SCAN_MAXW = 4;   // warps per generator block: NSEG <= 128
+
+template <int N, int LT>
+__global__ void __launch_bounds__(32 * SCAN_MAXW, 3) small_formscan_sym(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    __shared__ double sG[(1 + (LT > 0 ? LT : 16)) * NN];          // the block's generator (run-time L <= 16)
+    __shared__ double sT[SCAN_MAXW][2 * NN];                       // warp totals
+    const int g = blockIdx.x, seg = threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int G = p.G, NT = p.NT, L = LT > 0 ? LT : p.L;
+    for (int e = threadIdx.x; e < (1 + L) * NN; e += blockDim.x)
+        sG[e] = e < NN ? __ldg(&a.H0r[(size_t)e * G + g]) : __ldg(&a.Hcr[(size_t)(e - NN) * G + g]);
+    __syncthreads();
+    const bool valid = seg < a.NSEG;
+    const int n0 = seg * a.S, n1 = valid ? min(NT, n0 + a.S) : n0;
+    double Pr[NN], Pi[NN];
+#pragma unroll
+    for (int c = 0; c < NN; ++c) { Pr[c] = 0.0; Pi[c] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < N; ++i) Pr[i * N + i] = 1.0;               // lanes past the last segment carry the identity
+    for (int n = n0; n < n1; ++n) {
+        const double dt = p.tlist[n + 1] - p.tlist[n];
+        double Hs[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Hs[c] = sG[c];
+        auto add_control = [&](int l) {
+            double am = p.eps[l * NT + n];
+            if (p.shape) am *= p.shape[l * NT + n];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sG[NN + l * NN + c], Hs[c]);
+        };
+        if (LT > 0) {
+#pragma unroll
+            for (int l = 0; l < LT; ++l) add_control(l);
+        } else {
+            for (int l = 0; l < L; ++l) add_control(l);
+        }
+        double nrm = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
+            nrm = fmax(nrm, s);
+        }
+        double Cm[NN], Sm[NN];
+        sym_cos_sin<N>(Hs, dt, dt * nrm, Cm, Sm);
+        if (n == n0) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
+        } else {   // (C - iS)(Pr + i Pi)
+            double Tr[NN], Ti[NN];
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double ar = 0.0, ai = 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; ++k) {
+                        ar = fma(Cm[i * N + k], Pr[k * N + j], ar);
+                        ar = fma(Sm[i * N + k], Pi[k * N + j], ar);
+                        ai = fma(Cm[i * N + k], Pi[k * N + j], ai);
+                        ai = fma(-Sm[i * N + k], Pr[k * N + j], ai);
+                    }
+                    Tr[i * N + j] = ar;
+                    Ti[i * N + j] = ai;
+                }
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Tr[c]; Pi[c] = Ti[c]; }
+        }
+    }
+    // inclusive scan over the lanes: lane i ends with P_i P_{i-1} .. P_{first lane of the warp}
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        double Tr[NN], Ti[NN];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) {
+            Tr[c] = __shfl_up_sync(0xffffffffu, Pr[c], off);
+            Ti[c] = __shfl_up_sync(0xffffffffu, Pi[c], off);
+        }
+        if (lane >= off) {
+            double Nr[NN], Ni[NN];
+            cm_mm<N>(Nr, Ni, Pr, Pi, Tr, Ti);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Nr[c]; Pi[c] = Ni[c]; }
+        }
+    }
+    if (blockDim.x > 32) {   // earlier warps of the same generator
+        if (lane == 31) {
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { sT[w][c] = Pr[c]; sT[w][NN + c] = Pi[c]; }
+        }
+        __syncthreads();
+        for (int ww = w - 1; ww >= 0; --ww) {   // Q <- Q T_{w-1} T_{w-2} .. T_0
+            double Tr[NN], Ti[NN], Nr[NN], Ni[NN];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Tr[c] = sT[ww][c]; Ti[c] = sT[ww][NN + c]; }
+            cm_mm<N>(Nr, Ni, Pr, Pi, Tr, Ti);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) { Pr[c] = Nr[c]; Pi[c] = Ni[c]; }
+        }
+    }
+    if (valid) {
+        cplx* o = a.Pseg + (size_t)seg * NN * G + g;
+#pragma unroll
+        for (int c = 0; c < NN; ++c) o[(size_t)c * G] = mk(Pr[c], Pi[c]);
+    }
+}
+
+// tau_k = <tgt_k | Q_last Psi_k(0)>  (optimize.jl:752-753), final states, and the sums of reduce_tau -- single block,
+// strided fixed-order accumulation
+template <int N>
+__global__ void __launch_bounds__(1024) small_scan_tau_reduce(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    __shared__ double s_buf[32 * 4];
+    const int K = p.K, G = p.G, NT = p.NT;
+    const cplx* Ql = a.Pseg + (size_t)(a.NSEG - 1) * NN * G;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int g = p.gen[k];
+        cplx x[N], y[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = p.psi0[(size_t)i * K + k];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) cfma(acc, __ldg(&Ql[(size_t)(i * N + j) * G + g]), x[j]);
+            y[i] = acc;
+            p.psi[((size_t)NT * N + i) * K + k] = acc;             // fw_propagators[k].state after the sweep
+        }
+        cplx t = mk(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) cfmac(t, p.tgt[(size_t)i * K + k], y[i]);
+        p.tau[k] = t;
+        p.jb[k] = 0.0;
+        const double w = p.w ? p.w[k] : 1.0;
+        v[0] = fma(w, t.x, v[0]);
+        v[1] = fma(w, t.y, v[1]);
+        v[2] = fma(w, cnorm2(t), v[2]);
+    }
+    block_sum<4>(v, s_buf);
+    if (threadIdx.x == 0) { p.sums[0] = v[0]; p.sums[1] = v[1]; p.sums[2] = v[2]; p.sums[3] = 0.0; }
+}
+
+// thread per (k, seg), k fastest: everything the two boundary chains produced.  fwd_only: fw_storage boundaries only
+// (lazy read-back after a functional-only call).
+template <int N>
+__global__ void __launch_bounds__(128) small_scan_bounds(DevP p, SegArgs a, const cplx* __restrict__ chi_host, int fwd_only) {
+    constexpr int NN = N * N;
+    const int K = p.K, G = p.G, NT = p.NT;
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= (long long)K * a.NSEG) return;
+    const int k = (int)(idx % K), seg = (int)(idx / K);
+    const int g = p.gen[k];
+    const int nb = min(NT, (seg + 1) * a.S);
+    cplx Q[NN];
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Q[c] = __ldg(&a.Pseg[((size_t)seg * NN + c) * G + g]);
+    cplx x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = p.psi0[(size_t)i * K + k];
+    if (seg == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) st_cs(&p.psi[(size_t)i * K + k], x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        cplx acc = mk(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < N; ++j) cfma(acc, Q[i * N + j], x[j]);
+        st_cs(&p.psi[((size_t)nb * N + i) * K + k], acc);
+    }
+    if (fwd_only) return;
+    // chi_k(T): optimize.jl:845-855 with the analytic chi of J_T_sm / J_T_re / J_T_ss, or the host's chi
+    if (chi_host) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = chi_host[(size_t)k * N + i];
+    } else {
+        const double w = p.w ? p.w[k] : 1.0;
+        const double Kg = (double)p.Kglobal;
+        cplx c;
+        if (p.functional == 0) c = mk(w * p.sums[0] / (Kg * Kg), w * p.sums[1] / (Kg * Kg));
+        else if (p.functional == 1) c = mk(w / (2.0 * Kg), 0.0);
+        else { cplx t = p.tau[k]; c = mk(w * t.x / Kg, w * t.y / Kg); }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = cmul(c, p.tgt[(size_t)i * K + k]);
+    }
+    double rho = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) rho += cnorm2(x[i]);
+    rho = sqrt(rho);
+    if (!(rho >= p.chi_min_norm)) {   // optimize.jl:1021-1025
+        if (seg == 0 && atomicCAS(&p.flags->chi_bad_k, 0, k + 1) == 0) p.flags->chi_bad_rho = rho;
+        rho = 1.0;
+    }
+    const double ir = 1.0 / rho;
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = cscale(x[i], ir);
+    if (seg == 0) {
+        p.rho[k] = rho;
+#pragma unroll
+        for (int i = 0; i < N; ++i) p.chiT[(size_t)k * N + i] = x[i];
+    }
+    if (seg < a.NSEG - 1) {   // chi(end of seg) = Q_seg Q_last^dagger chi(T); the last segment ends at T itself
+        cplx y[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                cfmac(acc, __ldg(&a.Pseg[((size_t)(a.NSEG - 1) * NN + j * N + i) * G + g]), x[j]);   // (Q_last^dagger x)_i
+            y[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) cfma(acc, Q[i * N + j], y[j]);
+            x[i] = acc;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.chiE[((size_t)seg * N + i) * K + k] = x[i];
 }

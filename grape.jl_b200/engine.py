@@ -193,6 +193,13 @@ class GrapeEngine:
             self._check(-rc)
         return rc
 
+    def dense_concurrent(self):
+        """1: the last gradient call ran the forward sweep and the chi chain of the dense path concurrently."""
+        rc = int(self.lib.grape_b200_dense_concurrent(self._h))
+        if rc < 0:
+            self._check(-rc)
+        return rc
+
     def small_schedule(self):
         """0: not the segmented small path, 1: general, 2: Hermitian, 3: real-symmetric schedule served the last gradient."""
         rc = int(self.lib.grape_b200_small_schedule(self._h))

@@ -216,6 +216,12 @@ int64_t grape_b200_launch_count(const grape_b200_handle* h);
  * Both evaluate the same truncated series of the reference's GradGenerator step
  * (src/optimize.jl:880-896, docs/src/background.md:447-494). Negative: error code. */
 int grape_b200_gradient_form(grape_b200_handle* h);
+/* 1 if the last gradient call ran the forward sweep and the chi chain of the dense path CONCURRENTLY in one
+ * cooperative kernel (csrc/dense.cuh dense_chain<2, NS>: chi_k(T) = c_k tgt_k with a scalar c_k, so tgt_k is
+ * propagated backwards while Psi_k goes forwards and c_k enters the contraction afterwards; src/optimize.jl:845-855,
+ * 880-896), 0 if the sweeps ran one after the other (state running cost, host chi, sub-stepped steps, :taylor).
+ * Instrumentation; synchronises the stream. Negative: error code. */
+int grape_b200_dense_concurrent(grape_b200_handle* h);
 /* Which schedule of the small path (N <= 4) served the last gradient call (instrumentation; synchronises):
  *   0 = not the time-segmented small path (plain chains, sub-warp or dense path),
  *   1 = time-segmented, general generators (forward states read back from fw_storage),

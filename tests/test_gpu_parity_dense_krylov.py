@@ -259,3 +259,70 @@ def test_two_terms_per_barrier_full_width_oracle(lib_built):
     assert np.max(np.abs(G - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
     assert np.max(np.abs(e.final_states() - ref["final_states"])) <= 1e-12
     e.close()
+
+
+@pytest.mark.parametrize("functional,terms", [(gb.SM, 3), (gb.SS, 3), (gb.RE, 2), (gb.SM, 1)])
+def test_concurrent_forward_and_backward_chains(lib_built, functional, terms):
+    """dense_chain<2, NS> (csrc/dense.cuh): the forward sweep and the chi chain run at the same time in one cooperative
+    grid, chi_k(T) = c_k tgt_k being applied afterwards in the contraction.  Against the oracle, against the sequential
+    sweeps (GRAPE_B200_DENSE_CONCURRENT=0), with Taylor orders that differ between step n and step NT-1-n (pulse ramp:
+    the two directions need different numbers of grid barriers per iteration), weights, and call after call."""
+    N, K, NT = 72, 16, 9
+    w = np.linspace(0.5, 1.5, K)
+    p, eps = configs.c4_dense450(N=N, K=K, NT=NT, functional=functional, weights=w)
+    ramp = np.linspace(0.05, 2.5, NT)                      # ||H_n dt|| from ~0.1 to ~0.9: orders 9 .. 18
+    eps = (eps.reshape(2, NT) * ramp[None, :]).reshape(-1)
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    scale = np.max(np.abs(ref["G"]))
+    res = {}
+    for conc in (1, 0):
+        with _Env(GRAPE_B200_DENSE2=0, GRAPE_B200_DENSE_CONCURRENT=conc, GRAPE_B200_DENSE_TERMS=terms):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        for rep in range(2):
+            J = e.evaluate_gradient(G, eps)
+            assert e.dense_concurrent() == conc and e.gradient_form() > 0
+            assert abs(J - ref["J"]) <= 1e-10 and np.max(np.abs(e.tau_vals - ref["tau"])) <= 1e-10
+            assert np.max(np.abs(G - ref["G"])) <= 1e-10 * scale
+            assert abs(e.evaluate_functional(eps) - ref["J"]) <= 1e-10          # forward-only call in between
+        chi, rho = e.chi_states()
+        assert np.max(np.abs(chi - ref["chi_states"])) <= 1e-10 and np.max(np.abs(rho - ref["chi_norms"])) <= 1e-12
+        # split host API: forward, then backward with the (here: local = global) sums -> sequential sweeps
+        sums = e.forward(eps)
+        Gp = np.zeros_like(eps)
+        e.backward(sums, Gp)
+        assert e.dense_concurrent() == 0
+        assert np.max(np.abs(Gp - ref["grad_J_Tb"])) <= 1e-10 * scale
+        # sub-stepped pulses (||H dt|| > 1): the block recursion serves the call, then the concurrent chains again
+        big = eps * 6.0
+        refb = go.evaluate_gradient(go.from_problem(p), big)
+        Jb = e.evaluate_gradient(G, big)
+        assert e.gradient_form() == 0 and e.dense_concurrent() == 0
+        assert abs(Jb - refb["J"]) <= 1e-9 and np.max(np.abs(G - refb["G"])) <= 1e-9 * np.max(np.abs(refb["G"]))
+        J = e.evaluate_gradient(G, eps)
+        assert e.dense_concurrent() == conc and np.max(np.abs(G - ref["G"])) <= 1e-10 * scale
+        res[conc] = G.copy()
+        e.close()
+    assert np.max(np.abs(res[0] - res[1])) <= 1e-12 * scale
+
+
+def test_concurrent_chains_not_used_with_state_running_cost_or_host_chi(lib_built):
+    p, eps = configs.c5_dense1024(N=40, K=8, NT=6)                         # g_b: chi needs Psi(t_{n-1}) on its way back
+    with _Env(GRAPE_B200_DENSE2=0):
+        e = engine(p)
+    G = np.zeros_like(eps)
+    e.evaluate_gradient(G, eps)
+    assert e.dense_concurrent() == 0 and e.gradient_form() > 0
+    e.close()
+    p, eps = configs.c4_dense450(N=40, K=8, NT=6, functional=gb.HOST)
+    pr, _ = configs.c4_dense450(N=40, K=8, NT=6, functional=gb.SS)
+    ref = go.evaluate_gradient(go.from_problem(pr), eps)
+    with _Env(GRAPE_B200_DENSE2=0):
+        e = engine(p)
+    e.forward(eps)
+    tau = np.einsum("ki,ki->k", p.tgt.conj(), e.final_states())
+    Gp = np.zeros_like(eps)
+    e.backward_chi((tau / p.K)[:, None] * p.tgt, Gp)
+    assert e.dense_concurrent() == 0
+    assert np.max(np.abs(Gp - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
+    e.close()

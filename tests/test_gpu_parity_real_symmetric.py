@@ -91,12 +91,12 @@ def test_lane_mapping_and_functionals(lib_built, K):
 
 
 def test_ineligible_steps_fall_back_on_the_device(lib_built):
-    """a step with ||H dt|| > 0.0308 (more than 8 orders / sub-stepping) switches the whole call to the general
-    Hermitian kernel on the device; the flag follows the pulses call by call"""
+    """ROUND-1 kernels (GRAPE_B200_SYM_V=1): a step with ||H dt|| > 0.0308 (more than 8 orders / sub-stepping) switches
+    the whole call to the general Hermitian kernel on the device; the flag follows the pulses call by call"""
     p, eps = configs.random_problem(K=6, N=3, L=2, NT=25, seed=431, real=True, functional=gb.SM)
-    check(p, eps, schedule=2)[0].close()              # dt ~ 0.05, ||H|| ~ 3
+    check(p, eps, schedule=2, GRAPE_B200_SYM_V=1)[0].close()              # dt ~ 0.05, ||H|| ~ 3
     p.tlist[:] = p.tlist * 0.01
-    e = engine(p)
+    e = engine(p, GRAPE_B200_SYM_V=1)
     op = go.from_problem(p)
     G = np.zeros_like(eps)
     for amp, sched in ((1.0, 3), (40.0, 2), (0.5, 3), (40.0, 2), (1.0, 3)):
@@ -109,13 +109,55 @@ def test_ineligible_steps_fall_back_on_the_device(lib_built):
     e.close()
 
 
+@pytest.mark.parametrize("scan", [1, 0])
+def test_large_steps_are_sub_stepped_inside_the_real_kernel(lib_built, scan):
+    """Staged kernels (round 2): steps with ||H dt|| > 0.0308 are served by the real-symmetric gradient kernel itself,
+    as equal sub-steps of 8 orders, per warp and per step -- no call-wide switch to the complex kernel.  ||H dt|| up
+    to ~ 6 here (about 200 sub-steps), mixed with small steps in the same call."""
+    p, eps = configs.random_problem(K=6, N=3, L=2, NT=25, seed=431, real=True, functional=gb.SM)
+    check(p, eps, schedule=3, GRAPE_B200_SEG_SCAN=scan)[0].close()        # dt ~ 0.05, ||H|| ~ 3: every step sub-stepped
+    p.tlist[:] = p.tlist * 0.01
+    e = engine(p, GRAPE_B200_SEG_SCAN=scan)
+    op = go.from_problem(p)
+    G = np.zeros_like(eps)
+    rng = np.random.default_rng(3)
+    for amp in (1.0, 40.0, 0.5, 40.0, 1.0):
+        x = eps * amp
+        x[rng.integers(0, len(x), 7)] *= 300.0 / amp                       # a few very large steps among small ones
+        ref = go.evaluate_gradient(op, x)
+        J = e.evaluate_gradient(G, x)
+        assert e.small_schedule() == 3
+        assert abs(J - ref["J"]) <= RTOL
+        assert np.max(np.abs(G - ref["G"])) <= RTOL * max(np.max(np.abs(ref["G"])), 1e-6)
+    e.close()
+
+
+@pytest.mark.parametrize("NT,S", [(37, 2), (200, 2), (129, 1), (1000, 8), (1000, 11), (333, 16), (64, 64)])
+def test_scan_schedule_segment_counts(lib_built, NT, S):
+    """prefix products by the warp scan (csrc/small_sym.cuh small_formscan_sym): 1..4 warps per generator block,
+    ragged last segment, a forced segment length too short for one block (S = 1, 2 with NT > 128: widened)"""
+    p, eps = configs.random_problem(K=7, N=3, L=2, NT=NT, seed=470 + NT % 7, real=True, functional=gb.SS, G=3,
+                                    weights=np.linspace(0.5, 1.5, 7))
+    p.tlist[:] = p.tlist * 0.004
+    check(p, eps, GRAPE_B200_SEG_S=S)[0].close()
+
+
+@pytest.mark.parametrize("N,L", [(1, 1), (2, 1), (2, 3), (3, 4)])
+def test_scan_schedule_sizes_and_control_counts(lib_built, N, L):
+    p, eps = configs.random_problem(K=9, N=N, L=L, NT=150, seed=480 + N + L, real=True, functional=gb.SM, shaped=True)
+    p.tlist[:] = p.tlist * 0.004
+    check(p, eps)[0].close()
+    check(p, eps, GRAPE_B200_SEG_SCAN=0)[0].close()      # same kernels fed by the boundary chains
+
+
 def test_complex_hermitian_and_taylor_do_not_take_the_real_path(lib_built):
     p, eps = configs.random_problem(K=5, N=3, L=2, NT=19, seed=441, hermitian=True, functional=gb.SM)
     p.tlist[:] = p.tlist * 0.01
     check(p, eps, schedule=2)[0].close()
     p, eps = configs.random_problem(K=5, N=3, L=2, NT=19, seed=442, real=True, gradient_method=gb.TAYLOR)
     p.tlist[:] = p.tlist * 0.01
-    check(p, eps, schedule=2)[0].close()               # segment products still come from small_formseg_sym
+    check(p, eps, schedule=2)[0].close()               # boundaries still come from the real-symmetric scan kernels
+    check(p, eps, schedule=2, GRAPE_B200_SEG_SCAN=0)[0].close()
     p, eps = configs.random_problem(K=5, N=3, L=2, NT=19, seed=443, real=True)
     p.tlist[:] = p.tlist * 0.01
     check(p, eps, schedule=2, GRAPE_B200_SEG_REAL=0)[0].close()

@@ -44,6 +44,8 @@ SYMBOLS = {
     "grape_b200_last_error": (C.c_char_p, [_P]),
     "grape_b200_eval_f": (C.c_int, [_P, _D, _D, _D]),
     "grape_b200_eval_fg": (C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
+    "grape_b200_eval_f_amplitudes": (C.c_int, [_P, _D, _D, _D]),
+    "grape_b200_eval_fg_amplitudes": (C.c_int, [_P, _D, _D, _D, _D, _D]),
     "grape_b200_forward": (C.c_int, [_P, _D, _D, _D]),
     "grape_b200_backward": (C.c_int, [_P, _D, _D, _D, _D]),
     "grape_b200_backward_chi": (C.c_int, [_P, _D, _D, _D, _D]),

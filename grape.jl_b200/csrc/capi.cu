@@ -43,6 +43,7 @@ struct grape_b200_handle_impl {
     double* h_out;      // pinned mirror of d_out
     double* h_in;       // pinned staging: pulsevals[LNT] | sums[4]
     double* d_eps_own;  // handle-owned pulse buffer
+    double* d_damp;     // handle-owned [L*NT] d a / d eps of amplitude mode (allocated on first use)
     cplx* d_chi_host;   // [K*N] user chi for backward_chi
     cplx* d_tmp;        // gather scratch
     size_t tmp_elems;
@@ -68,6 +69,8 @@ struct grape_b200_handle_impl {
     bool seg_fuse;        // small path, segmented: fused propagator formation + segment product (small_formseg)
     bool seg_scan;        // small path, real-symmetric generators: prefix products by a parallel scan, no boundary chains
     bool bounds_done;     // scan schedule: the segment boundaries of fw_storage hold the states of the current pulses
+    bool chain_dual;      // chain schedule: the forward phase of this call carried the targets backwards too (small_segchain_dual)
+    bool chib_done;       // scan schedule: chiE / rho / chiT were written by small_scan_bounds for the current backward call
     int sym_v;            // 2: operators staged in shared memory (small_*_sym2, default); 1: round-1 kernels (GRAPE_B200_SYM_V=1)
     int sym_occ;          // resident CTAs per SM small_seggrad_sym is compiled for (3; GRAPE_B200_SYM_OCC=2: no spills, 8 warps)
     bool seg_real;        // seg_herm and every generator real (symmetric): real-arithmetic kernels of small_sym.cuh
@@ -282,7 +285,9 @@ int small_setup(H* h, const grape_b200_problem* d) {
                 const long long nseg = (NT + s_ - 1) / s_;
                 const long long warps = KGR * ((nseg + SPW - 1) / SPW);
                 full = warps >= resident;
-                return (double)((warps + resident - 1) / resident) * s_ + 0.26 * (double)nseg;
+                // warps drain continuously rather than in lock-step waves: fractional waves, plus half a segment of tail
+                // (measured on C3, profiles/r2_s1_c3_sweep.txt: S = 20..25 beats the S = 38 of a whole-wave model by 2 %)
+                return std::max(1.0, (double)warps / (double)resident) * s_ + 0.5 * s_ + 0.26 * (double)nseg;
             };
             bool full = false;
             double best = cost(S, full);
@@ -308,12 +313,23 @@ int small_setup(H* h, const grape_b200_problem* d) {
         // short segments cost nothing extra, and the measured optimum of formation + contraction is at the shortest
         // segments that keep the block full (profiles/r2_s1_c3_sweep.txt): NSEG ~ 128 for shards up to 2048
         // trajectories, ~ 64 above.  GRAPE_B200_SEG_SCAN=0 keeps the chains.
-        h->seg_scan = h->seg_real && h->sym_v != 1 && h->seg_fuse && L <= 16 &&
-                      !(getenv("GRAPE_B200_SEG_SCAN") && atoi(getenv("GRAPE_B200_SEG_SCAN")) == 0);
+        // Measured (profiles/r2_s2_c3_sweep.txt): the scan's extra products (+10 % formation work) pay off when the
+        // sequential chains are a visible share of the step, i.e. for shards of up to 2048 trajectories (0.133 ->
+        // 0.103 ms at K = 512); at K = 4096 the chains are 7 % of the step and stay.  GRAPE_B200_SEG_SCAN=1 / 0 forces.
+        h->seg_scan = h->seg_real && h->sym_v != 1 && h->seg_fuse && L <= 16 && K <= 2048;
+        if (const char* e = getenv("GRAPE_B200_SEG_SCAN"))
+            h->seg_scan = h->seg_real && h->sym_v != 1 && h->seg_fuse && L <= 16 && atoi(e) != 0;
         if (h->seg_scan) {
-            const int target = K <= 2048 ? 128 : 64;
+            const long long KGR = (K + a.BKL - 1) / a.BKL;
+            const int target = KGR >= 64 ? 64 : 96;     // segments per generator: measured optimum 63 (K = 2048), 91 (K <= 1024)
             S = (NT + target - 1) / target;
             if (S < 2) S = 2;
+        }
+        if (h->seg_scan) {
+            if (int rc = dev_alloc(h, &a.tau_part, (size_t)((K + 255) / 256) * 4)) return rc;
+            if (int rc = dev_alloc(h, &a.tau_ticket, 1)) return rc;
+            CUDA_TRY(h, cudaMemset(a.tau_ticket, 0, sizeof(int)));
+            a.scan = 1;
         }
         if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
         a.S = S < 2 ? 2 : (S > 128 ? 128 : S);
@@ -404,7 +420,7 @@ void seg_formseg_t(H* h) {
 }
 template <int N>
 void seg_scan_tau_t(H* h) {
-    small_scan_tau_reduce<(N <= 3 ? N : 1)><<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p, h->seg);
+    small_scan_tau<(N <= 3 ? N : 1)><<<(h->p.K + 255) / 256, 256, 0, h->stream>>>(h->p, h->seg);
     h->launches++;
 }
 template <int N>
@@ -416,6 +432,11 @@ void seg_scan_bounds_t(H* h, const cplx* chi_host, int fwd_only) {
 template <int N>
 void seg_chain_fwd_t(H* h) {
     small_segchain_fwd<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg);
+    h->launches++;
+}
+template <int N>
+void seg_chain_dual_t(H* h) {
+    small_segchain_dual<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg);
     h->launches++;
 }
 template <int N>
@@ -434,6 +455,12 @@ bool seg_fused(const H* h) { return h->seg_on && h->seg_fuse; }
 // the real-symmetric gradient kernel may serve this call: its eligibility flag was written by small_formseg_sym
 bool seg_real_active(const H* h) {
     return h->seg_real && seg_fused(h) && h->p.grad_method == 0 && !h->p.taugrads;
+}
+// gradient calls served by the staged real-symmetric kernel on the chain schedule: both boundary chains in one pass
+bool chain_dual_ok(const H* h) {
+    return h->seg_on && !h->seg_scan && h->p.N <= 3 && h->sym_v != 1 && seg_real_active(h) &&
+           h->p.functional != GRAPE_B200_JT_HOST &&
+           !(getenv("GRAPE_B200_CHAIN_DUAL") && atoi(getenv("GRAPE_B200_CHAIN_DUAL")) == 0);
 }
 template <int N, int LCMAX, bool HERM>
 void seg_grad_launch(H* h, const int* run_if) {
@@ -477,6 +504,14 @@ void seg_grad_t(H* h) {
             h->launches++;
             return;
         }
+    }
+    if (h->seg_scan && !h->chib_done) {   // general kernel after a fast-path backward call (tau_grads dump)
+        seg_scan_bounds_t<N>(h, h->seg.chi_host, 0);
+        h->bounds_done = h->chib_done = true;
+    } else if (h->seg_on && !h->seg_scan && !h->chib_done) {   // ... after a one-pass chain call: the normalised chi chain
+        seg_chain_bwd_t<N>(h, nullptr);
+        h->seg.scan = 0;
+        h->chib_done = true;
     }
     if (h->seg_herm) seg_grad_launch<N, LCMAX, true>(h, run_if);
     else seg_grad_launch<N, LCMAX, false>(h, run_if);
@@ -541,10 +576,17 @@ void run_forward(H* h, bool need_storage = true, bool with_backward = false) {
                 SMALL_DISPATCH(h->p.N, seg_scan_tau_t<1>(h), seg_scan_tau_t<2>(h), seg_scan_tau_t<3>(h), seg_scan_tau_t<3>(h));
                 h->interior_done = false;
                 h->bounds_done = false;
+                h->chib_done = false;
                 break;
             }
             if (h->seg_on) {
-                SMALL_DISPATCH(h->p.N, seg_chain_fwd_t<1>(h), seg_chain_fwd_t<2>(h), seg_chain_fwd_t<3>(h), seg_chain_fwd_t<4>(h));
+                // gradient call served by the staged real-symmetric kernel: both boundary chains in one pass
+                h->chain_dual = with_backward && chain_dual_ok(h);
+                if (h->chain_dual) {
+                    SMALL_DISPATCH(h->p.N, seg_chain_dual_t<1>(h), seg_chain_dual_t<2>(h), seg_chain_dual_t<3>(h), seg_chain_dual_t<3>(h));
+                } else {
+                    SMALL_DISPATCH(h->p.N, seg_chain_fwd_t<1>(h), seg_chain_fwd_t<2>(h), seg_chain_fwd_t<3>(h), seg_chain_fwd_t<4>(h));
+                }
                 h->interior_done = false;
                 if (need_storage && !h->seg_herm) run_fill_interior(h);
                 break;
@@ -579,12 +621,26 @@ void run_backward(H* h, const cplx* chi_host) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
             if (h->seg_on && h->seg_scan) {
-                SMALL_DISPATCH(h->p.N, seg_scan_bounds_t<1>(h, chi_host, 0), seg_scan_bounds_t<2>(h, chi_host, 0),
-                               seg_scan_bounds_t<3>(h, chi_host, 0), seg_scan_bounds_t<3>(h, chi_host, 0));
-                h->bounds_done = true;
+                // the real-symmetric gradient kernel derives its boundary states from the prefix products itself; the
+                // general kernels (:taylor, tau_grads dump) read the arrays small_scan_bounds fills
+                h->seg.chi_host = chi_host;
+                h->seg.scan = 1;
+                h->chib_done = false;
+                if (!seg_real_active(h)) {
+                    SMALL_DISPATCH(h->p.N, seg_scan_bounds_t<1>(h, chi_host, 0), seg_scan_bounds_t<2>(h, chi_host, 0),
+                                   seg_scan_bounds_t<3>(h, chi_host, 0), seg_scan_bounds_t<3>(h, chi_host, 0));
+                    h->bounds_done = h->chib_done = true;
+                }
+                break;
+            }
+            if (h->seg_on && h->chain_dual && !chi_host && seg_real_active(h)) {
+                h->seg.scan = 2;     // chiE already holds the propagated targets; the gradient kernel applies c_k / rho_k
+                h->chib_done = false;
                 break;
             }
             if (h->seg_on) {
+                h->seg.scan = 0;
+                h->chib_done = true;
                 if (!h->seg_herm) run_fill_interior(h);
                 SMALL_DISPATCH(h->p.N, seg_chain_bwd_t<1>(h, chi_host), seg_chain_bwd_t<2>(h, chi_host),
                                seg_chain_bwd_t<3>(h, chi_host), seg_chain_bwd_t<4>(h, chi_host));
@@ -735,7 +791,8 @@ int eval_via_graph(H* h, const double* pulsevals, bool grad) {
     h->launches += gl;
     // the captured sequence of eval_f leaves the interior of fw_storage unfilled
     if (h->seg_on || h->wseg_on) h->interior_done = grad && !h->seg_herm;
-    if (h->seg_scan) h->bounds_done = grad;
+    if (h->seg_scan) h->bounds_done = h->chib_done = grad && !seg_real_active(h);
+    else if (h->seg_on) { h->chain_dual = grad && chain_dual_ok(h); h->chib_done = grad && !h->chain_dual; }
     if (h->path == GRAPE_B200_PATH_SMALL)   // same bookkeeping as run_formU (not executed on a graph replay)
         h->U_valid = !(seg_fused(h) && !h->seg.store_U);
     return 1;
@@ -839,12 +896,12 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
 
     grape_b200_handle* h = new grape_b200_handle();
     memset(&h->p, 0, sizeof(DevP));
-    h->d_out = nullptr; h->h_out = nullptr; h->h_in = nullptr; h->d_chi_host = nullptr;
+    h->d_out = nullptr; h->h_out = nullptr; h->h_in = nullptr; h->d_chi_host = nullptr; h->d_damp = nullptr;
     h->d_tmp = nullptr; h->tmp_elems = 0; h->stream = nullptr;
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->taugrads_valid = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
-    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->seg_scan = false; h->bounds_done = false; h->d_taugrads = nullptr; h->taugrads_valid = false;
+    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->seg_scan = false; h->bounds_done = false; h->chib_done = false; h->chain_dual = false; h->d_taugrads = nullptr; h->taugrads_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     memset(&h->xd, 0, sizeof h->xd); h->xchg_on = false; h->xchg_mode = false; h->xchg_fonly = false;
     h->xchg_buf = nullptr; h->xchg_bytes = 0; h->launched_via_graph = false; h->launch_l0 = 0;
@@ -882,7 +939,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
         double* q;
         TRYC(dev_upload(h, &q, d->tlist, (size_t)p.NT + 1)); p.tlist = q;
         TRYC(dev_alloc(h, &h->d_eps_own, (size_t)LNT)); p.eps = h->d_eps_own;
-        if (d->shape) { TRYC(dev_upload(h, &q, d->shape, (size_t)LNT)); p.shape = q; }
+        if (d->shape) { TRYC(dev_upload(h, &q, d->shape, (size_t)LNT)); p.shape = q; p.dshape = q; }
         if (d->weights) { TRYC(dev_upload(h, &q, d->weights, (size_t)K)); p.w = q; }
         std::vector<int> gen(K);
         for (int k = 0; k < K; ++k) {
@@ -981,6 +1038,69 @@ int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G,
     if (int rc = eval_launch(h, pulsevals, true)) return rc;
     if (int rc = eval_wait(h, true)) return rc;
     return eval_fg_copy_out(h, G, J_parts, tau, grad_J_Tb, grad_J_a);
+}
+
+// ---- amplitude mode: non-linear controls / per-term amplitudes (reference src/workspace.jl:283-285 get_control_derivs,
+// src/optimize.jl:946-951 incl. the isnothing(mu) -> 0 branch).  The descriptor's L "controls" are amplitude SLOTS:
+// H_n = H0 + sum_i ampl[i][n] Hc_i and mu_{i,n} = dampl[i][n] Hc_i, both evaluated by the host from its closures
+// (L*NT scalar evaluations per call).  G_slots[i][n] is the gradient with respect to the control value behind slot i
+// THROUGH that slot; the host adds the slots of one control.  Direct launches (no graph: the kernel parameters differ).
+static int eval_amplitudes(grape_b200_handle* h, const double* ampl, const double* dampl, bool grad) {
+    if (h->p.ja_kind != GRAPE_B200_JA_NONE) {
+        h->err = "amplitude mode: J_a acts on the control values, which the library does not see -- evaluate it on the host "
+                 "(ja_kind must be GRAPE_B200_JA_NONE)";
+        return GRAPE_B200_EINVAL;
+    }
+    if (h->p.shape) {
+        h->err = "amplitude mode: the handle must be created without a static shape (fold it into ampl / dampl)";
+        return GRAPE_B200_EINVAL;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int LNT = h->LNT;
+    if (grad && !h->d_damp)
+        if (int rc = dev_alloc(h, &h->d_damp, (size_t)LNT)) return rc;
+    h->xchg_mode = true;
+    h->launch_l0 = h->launches;
+    h->launched_via_graph = false;
+    const double* shape0 = h->p.shape;
+    const double* dshape0 = h->p.dshape;
+    rec(h, 0);
+    if (int rc = upload_pulses(h, ampl)) return rc;        // eps <- the amplitudes themselves
+    if (grad) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_damp, dampl, sizeof(double) * LNT, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->p.shape = nullptr;
+    h->p.dshape = grad ? h->d_damp : nullptr;
+    run_xchg_begin(h, grad);
+    run_formU(h); rec(h, 1);
+    run_forward(h, grad, false); rec(h, 2);
+    rec(h, 3);
+    if (grad) { run_backward(h, nullptr); rec(h, 4); run_gradient(h); }
+    else rec(h, 4);
+    run_finalize(h, grad); rec(h, 5);
+    h->p.shape = shape0;
+    h->p.dshape = dshape0;
+    if (int rc = download_enqueue(h)) return rc;
+    return eval_wait(h, grad);
+}
+
+int grape_b200_eval_f_amplitudes(grape_b200_handle* h, const double* ampl, double* J_parts, double* tau) {
+    if (!h || !ampl) return GRAPE_B200_EINVAL;
+    if (int rc = eval_amplitudes(h, ampl, nullptr, false)) return rc;
+    if (h->p.functional == GRAPE_B200_JT_HOST) h->h_out[h->off_J] = 0.0 / 0.0;
+    copy_out_common(h, J_parts, tau);
+    return check_flags(h);
+}
+
+int grape_b200_eval_fg_amplitudes(grape_b200_handle* h, const double* ampl, const double* dampl, double* G_slots,
+                                  double* J_parts, double* tau) {
+    if (!h || !ampl || !dampl || !G_slots) return GRAPE_B200_EINVAL;
+    if (h->p.functional == GRAPE_B200_JT_HOST) {
+        h->err = "eval_fg_amplitudes needs a built-in functional";
+        return GRAPE_B200_EINVAL;
+    }
+    if (int rc = eval_amplitudes(h, ampl, dampl, true)) return rc;
+    return eval_fg_copy_out(h, G_slots, J_parts, tau, nullptr, nullptr);
 }
 
 int grape_b200_forward(grape_b200_handle* h, const double* pulsevals, double* tau, double* sums) {

@@ -107,7 +107,9 @@ struct DevP {
     double lambda_a, lambda_b, chi_min_norm, taylor_tol;
     const double* tlist;   // [NT+1]
     const double* eps;     // [L*NT] pulse values (device copy of `pulsevals`)
-    const double* shape;   // [L*NT] or nullptr
+    const double* shape;   // [L*NT] or nullptr: the amplitude of control l at step n is eps * shape
+    const double* dshape;  // [L*NT] or nullptr (= 1): d amplitude / d eps; == shape for ShapedAmplitude, the host's
+                           // d a / d eps in amplitude mode (grape_b200_eval_fg_amplitudes: eps holds a itself, shape is off)
     const int* gen;        // [K]
     const cplx* H0;        // path-specific layout
     const cplx* Hc;

@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_backward(DevP p, Dense
                                 int c1[1] = {chi0 + (pg + g) * 8 - l * Kp};
                                 DAcc a1[1];
                                 a1[0] = acc[g];
-                                const double sl = p.shape ? p.shape[l * NT + n] : 1.0;
+                                const double sl = p.dshape ? p.dshape[l * NT + n] : 1.0;
                                 if (d.mu_smem) {
                                     const double* Ml = Mu_s + (size_t)(l * 2) * 8 * MS;
                                     dense_mma_slice<1, true, 8>(Ml, Ml + 8 * MS, MS, sl, src, src + bplane, Cb, c1, 1, kbeg, kend, a1);

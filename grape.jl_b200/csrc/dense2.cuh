@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_backward(DevP p, DenseDe
         const double* Hn = d2.Hn[n & 1];
         double sl[LB];
 #pragma unroll
-        for (int l = 0; l < LB; ++l) sl[l] = (l < L && p.shape) ? p.shape[l * NT + n] : 1.0;
+        for (int l = 0; l < LB; ++l) sl[l] = (l < L && p.dshape) ? p.dshape[l * NT + n] : 1.0;
         int m, s;
         dense_plan(p, d, n, dt, m, s);
         const int nsub = 1 << s;

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) kry_reduce(DevP p, DenseDev d, KryDev kd)
         const int l = idx / p.NT, n = idx % p.NT;
         double s = 0.0;
         for (int r = 0; r < kd.TT; ++r) s += kd.tilepart[((size_t)n * kd.TT + r) * p.L + l];
-        const double sl = p.shape ? p.shape[idx] : 1.0;
+        const double sl = p.dshape ? p.dshape[idx] : 1.0;
         p.partial[idx] = (p.tlist[n + 1] - p.tlist[n]) * sl * s;
     }
 }

@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) small_gradient(DevP p, int l0, int BK) {
 #pragma unroll
     for (int l = 0; l < LC; ++l) {
         double sl = sc;
-        if (p.shape) sl *= p.shape[(l0 + l) * NT + nn];
+        if (p.dshape) sl *= p.dshape[(l0 + l) * NT + nn];
 #pragma unroll
         for (int i = 0; i < N; ++i)
 #pragma unroll

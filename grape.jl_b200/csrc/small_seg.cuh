@@ -66,6 +66,11 @@ struct SegArgs {
     const double* H0r;   // [NN][G]
     const double* Hcr;   // [L][NN][G]
     int* notfast;        // [1] set by small_formseg_sym when a step needs > SEG_MMAX orders or sub-stepping
+    // scan schedule (small_sym.cuh): Pseg holds the PREFIX products Q_seg = P_seg .. P_0
+    int scan;            // the gradient kernel derives its boundary states from Q itself (no chains, no bounds kernel)
+    const cplx* chi_host;// host chi of the current backward call (nullptr: analytic chi of the built-in functional)
+    double* tau_part;    // [blocks][4] partial sums of small_scan_tau
+    int* tau_ticket;     // [1] arrival counter of small_scan_tau (left at 0)
 };
 
 // ---------------------------------------------------------------------------
@@ -286,6 +291,85 @@ __global__ void __launch_bounds__(64) small_segchain_bwd(DevP p, SegArgs a, cons
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// B1 + B2 in one pass (gradient calls with a built-in functional): chi_k(T) = c_k tgt_k with a scalar c_k
+// (optimize.jl:845-855), and the backward chain is linear, so tgt_k is carried backwards over the segment
+// boundaries WHILE Psi_k is carried forwards -- two independent dependency chains per thread, the latency of one.
+// chiE receives the propagated RAW targets; the gradient kernel multiplies by c_k / rho_k (SegArgs::scan == 2).
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(64) small_segchain_dual(DevP p, SegArgs a) {
+    constexpr int NN = N * N;
+    const int K = p.K, G = p.G, NT = p.NT;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int g = p.gen[k];
+    const cplx* Pg = a.Pseg + g;
+    cplx psi[N], y[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        psi[i] = p.psi0[(size_t)i * K + k];
+        st_cs(&p.psi[(size_t)i * K + k], psi[i]);
+        y[i] = p.tgt[(size_t)i * K + k];
+    }
+    constexpr int CH = 2;
+    for (int s0 = 0; s0 < a.NSEG; s0 += CH) {
+        cplx Pf[CH][NN], Pb[CH][NN];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int sf = s0 + u, sb = a.NSEG - 1 - sf;
+            if (sf < a.NSEG) {
+#pragma unroll
+                for (int c = 0; c < NN; ++c) Pf[u][c] = __ldg(&Pg[((size_t)sf * NN + c) * G]);
+                if (sb > 0) {
+#pragma unroll
+                    for (int c = 0; c < NN; ++c) Pb[u][c] = __ldg(&Pg[((size_t)sb * NN + c) * G]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const int sf = s0 + u, sb = a.NSEG - 1 - sf;
+            if (sf < a.NSEG) {
+                cplx nw[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) cfma(acc, Pf[u][i * N + j], psi[j]);
+                    nw[i] = acc;
+                }
+                const int nb = min(NT, (sf + 1) * a.S);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    psi[i] = nw[i];
+                    st_cs(&p.psi[((size_t)nb * N + i) * K + k], psi[i]);
+                }
+                // the target at the END of segment sb, then through P_sb^dagger
+#pragma unroll
+                for (int i = 0; i < N; ++i) a.chiE[((size_t)sb * N + i) * K + k] = y[i];
+                if (sb > 0) {
+                    cplx ny[N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) cfmac(acc, Pb[u][j * N + i], y[j]);
+                        ny[i] = acc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) y[i] = ny[i];
+                }
+            }
+        }
+    }
+    cplx acc = mk(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < N; ++i) cfmac(acc, p.tgt[(size_t)i * K + k], psi[i]);
+    p.tau[k] = acc;
+    p.jb[k] = 0.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -580,7 +664,7 @@ __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0, 
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 double sl = sc;
-                if (p.shape) sl *= p.shape[(l0 + l) * NT + nn];
+                if (p.dshape) sl *= p.dshape[(l0 + l) * NT + nn];
                 // E_pq = i*sl*conj(Hc[q][p]);  Tr(E^dagger M) = sum conj(E_pq) M_pq
                 cplx acc = mk(0.0, 0.0);
 #pragma unroll
@@ -608,7 +692,7 @@ __global__ void __launch_bounds__(128) small_seggrad(DevP p, SegArgs a, int l0, 
 #pragma unroll
             for (int l = 0; l < LC; ++l) {
                 double sl = sc;
-                if (p.shape) sl *= p.shape[(l0 + l) * NT + nn];
+                if (p.dshape) sl *= p.dshape[(l0 + l) * NT + nn];
 #pragma unroll
                 for (int i = 0; i < N; ++i)
 #pragma unroll

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(128, MINB) small_seggrad_sym(DevP p, SegArgs a
         }
         for (int l = 0; l < p.L; ++l) {
             double sl = dt * rho;
-            if (p.shape) sl *= p.shape[l * NT + nn];
+            if (p.dshape) sl *= p.dshape[l * NT + nn];
             double acc = 0.0;
 #pragma unroll
             for (int c = 0; c < NN; ++c) acc = fma(__ldg(&a.Hcr[((size_t)l * NN + c) * G + g]), IM[c], acc);
@@ -498,14 +498,113 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs 
     const int kk = k < K ? k : K - 1;
     const int sseg = seg < a.NSEG ? seg : a.NSEG - 1;
     const int n0 = sseg * a.S, n1 = min(NT, n0 + a.S);
-    const double rho = p.rho[kk];
+    double rho = a.scan ? 1.0 : p.rho[kk];   // scan schedules: computed in the prologue below
     sym_stage<N>(p, a, p.gen[kk], L, sH);
 
     cplx chi[N], psi[N];
+    if (a.scan == 2) {
+        // one-pass boundary chains (small_segchain_dual): chiE holds the propagated raw target, chi = (c_k / rho_k) x it
+        const double w = p.w ? p.w[kk] : 1.0;
+        const double Kg = (double)p.Kglobal;
+        cplx c;
+        if (p.functional == 0) c = mk(w * p.sums[0] / (Kg * Kg), w * p.sums[1] / (Kg * Kg));
+        else if (p.functional == 1) c = mk(w / (2.0 * Kg), 0.0);
+        else { cplx t = p.tau[kk]; c = mk(w * t.x / Kg, w * t.y / Kg); }
+        cplx x[N];
+        double rn = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        chi[i] = a.chiE[((size_t)sseg * N + i) * K + kk];
-        psi[i] = ld_cs(&p.psi[((size_t)n1 * N + i) * K + kk]);   // segment boundary written by the forward chain
+        for (int i = 0; i < N; ++i) { x[i] = cmul(c, p.tgt[(size_t)i * K + kk]); rn += cnorm2(x[i]); }
+        rn = sqrt(rn);
+        if (!(rn >= p.chi_min_norm)) {   // optimize.jl:1021-1025
+            if (live && seg == 0 && atomicCAS(&p.flags->chi_bad_k, 0, k + 1) == 0) p.flags->chi_bad_rho = rn;
+            rn = 1.0;
+        }
+        rho = rn;
+        const double ir = 1.0 / rn;
+        if (live && seg == 0) {
+            p.rho[k] = rn;
+#pragma unroll
+            for (int i = 0; i < N; ++i) p.chiT[(size_t)k * N + i] = cscale(x[i], ir);
+        }
+        const cplx f = cscale(c, ir);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            chi[i] = cmul(f, a.chiE[((size_t)sseg * N + i) * K + kk]);
+            psi[i] = ld_cs(&p.psi[((size_t)n1 * N + i) * K + kk]);
+        }
+    } else if (a.scan) {
+        // scan schedule: both boundary states of this (k, seg) straight from the prefix products Q (4 mat-vecs):
+        //   Psi(end of seg) = Q_seg Psi(0),  chi(end of seg) = Q_seg Q_last^dagger chi(T)   (every P is unitary)
+        const int G = p.G, g = p.gen[kk];
+        cplx Q[NN], x[N];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Q[c] = __ldg(&a.Pseg[((size_t)sseg * NN + c) * G + g]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = p.psi0[(size_t)i * K + kk];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cplx acc = mk(0.0, 0.0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) cfma(acc, Q[i * N + j], x[j]);
+            psi[i] = acc;
+        }
+        if (a.chi_host) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = a.chi_host[(size_t)kk * N + i];
+        } else {   // optimize.jl:845-855 with the analytic chi of J_T_sm / J_T_re / J_T_ss
+            const double w = p.w ? p.w[kk] : 1.0;
+            const double Kg = (double)p.Kglobal;
+            cplx c;
+            if (p.functional == 0) c = mk(w * p.sums[0] / (Kg * Kg), w * p.sums[1] / (Kg * Kg));
+            else if (p.functional == 1) c = mk(w / (2.0 * Kg), 0.0);
+            else { cplx t = p.tau[kk]; c = mk(w * t.x / Kg, w * t.y / Kg); }
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = cmul(c, p.tgt[(size_t)i * K + kk]);
+        }
+        double rn = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) rn += cnorm2(x[i]);
+        rn = sqrt(rn);
+        if (!(rn >= p.chi_min_norm)) {   // optimize.jl:1021-1025
+            if (live && seg == 0 && atomicCAS(&p.flags->chi_bad_k, 0, k + 1) == 0) p.flags->chi_bad_rho = rn;
+            rn = 1.0;
+        }
+        rho = rn;
+        const double ir = 1.0 / rn;
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = cscale(x[i], ir);
+        if (live && seg == 0) {
+            p.rho[k] = rn;
+#pragma unroll
+            for (int i = 0; i < N; ++i) p.chiT[(size_t)k * N + i] = x[i];
+        }
+        if (sseg < a.NSEG - 1) {
+            cplx y[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    cfmac(acc, __ldg(&a.Pseg[((size_t)(a.NSEG - 1) * NN + j * N + i) * G + g]), x[j]);   // (Q_last^dagger x)_i
+                y[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                for (int j = 0; j < N; ++j) cfma(acc, Q[i * N + j], y[j]);
+                chi[i] = acc;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) chi[i] = x[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            chi[i] = a.chiE[((size_t)sseg * N + i) * K + kk];
+            psi[i] = ld_cs(&p.psi[((size_t)n1 * N + i) * K + kk]);   // segment boundary written by the forward chain
+        }
     }
     double* const part = p.partial + (size_t)kg * L * NT;
     const bool writer = tk == 0 && seg < a.NSEG;
@@ -553,7 +652,7 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs 
         }
         auto one_control = [&](int l) {
             double sl = dt * rho;
-            if (p.shape) sl *= p.shape[l * NT + nn];
+            if (p.dshape) sl *= p.dshape[l * NT + nn];
             double acc = 0.0;
 #pragma unroll
             for (int c = 0; c < NN; ++c) acc = fma(sH[(NN + l * NN + c) * SYM_BD + threadIdx.x], IM[c], acc);
@@ -719,16 +818,19 @@ __global__ void __launch_bounds__(32 * SCAN_MAXW, 3) small_formscan_sym(DevP p, 
     }
 }
 
-// tau_k = <tgt_k | Q_last Psi_k(0)>  (optimize.jl:752-753), final states, and the sums of reduce_tau -- single block,
-// strided fixed-order accumulation
+// tau_k = <tgt_k | Q_last Psi_k(0)>  (optimize.jl:752-753), final states, and the sums of reduce_tau: thread per
+// trajectory, one partial sum per block, the last block to arrive adds the partials in block order (fixed order:
+// deterministic run to run)
 template <int N>
-__global__ void __launch_bounds__(1024) small_scan_tau_reduce(DevP p, SegArgs a) {
+__global__ void __launch_bounds__(256) small_scan_tau(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     __shared__ double s_buf[32 * 4];
+    __shared__ int s_last;
     const int K = p.K, G = p.G, NT = p.NT;
     const cplx* Ql = a.Pseg + (size_t)(a.NSEG - 1) * NN * G;
     double v[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) {
         const int g = p.gen[k];
         cplx x[N], y[N];
 #pragma unroll
@@ -747,12 +849,25 @@ __global__ void __launch_bounds__(1024) small_scan_tau_reduce(DevP p, SegArgs a)
         p.tau[k] = t;
         p.jb[k] = 0.0;
         const double w = p.w ? p.w[k] : 1.0;
-        v[0] = fma(w, t.x, v[0]);
-        v[1] = fma(w, t.y, v[1]);
-        v[2] = fma(w, cnorm2(t), v[2]);
+        v[0] = w * t.x;
+        v[1] = w * t.y;
+        v[2] = w * cnorm2(t);
     }
     block_sum<4>(v, s_buf);
-    if (threadIdx.x == 0) { p.sums[0] = v[0]; p.sums[1] = v[1]; p.sums[2] = v[2]; p.sums[3] = 0.0; }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a.tau_part[(size_t)blockIdx.x * 4 + q] = v[q];
+        __threadfence();
+        s_last = atomicAdd(a.tau_ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 4) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&a.tau_part[(size_t)b * 4 + threadIdx.x]);
+        p.sums[threadIdx.x] = threadIdx.x == 3 ? 0.0 : s;
+        if (threadIdx.x == 0) *a.tau_ticket = 0;
+    }
 }
 
 // thread per (k, seg), k fastest: everything the two boundary chains produced.  fwd_only: fw_storage boundaries only

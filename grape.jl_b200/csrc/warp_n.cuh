@@ -352,7 +352,7 @@ __global__ void warp_gradient(DevP p, int l0, int spb) {
     const double sc = dt * ldexp(1.0, -s);
     double scl[LC];
 #pragma unroll
-    for (int l = 0; l < LC; ++l) scl[l] = p.shape ? sc * p.shape[(l0 + l) * NT + n] : sc;
+    for (int l = 0; l < LC; ++l) scl[l] = p.dshape ? sc * p.dshape[(l0 + l) * NT + n] : sc;
     const cplx* Hcl = Hc + (size_t)l0 * NN;
 
     cplx asum = own ? ld_cs(&p.chi[((size_t)(n + 1) * K + k) * N + r]) : mk(0.0, 0.0);

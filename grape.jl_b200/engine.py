@@ -127,6 +127,23 @@ class GrapeEngine:
         self.fg_calls += 1
         return float(np.sum(self.J_parts))
 
+    # -- amplitude mode: non-linear controls / per-term amplitudes (include/grape_b200.h) ------------------
+    def evaluate_functional_amplitudes(self, ampl):
+        a = self._pulses(ampl, self.L * self.NT)
+        self._check(self.lib.grape_b200_eval_f_amplitudes(self._h, _dp(a), _dp(self.J_parts),
+                                                          _dp(self.tau_vals.view(np.float64))))
+        self.f_calls += 1
+        return float(np.sum(self.J_parts))
+
+    def evaluate_gradient_amplitudes(self, G_slots, ampl, dampl):
+        a = self._pulses(ampl, self.L * self.NT)
+        da = self._pulses(dampl, self.L * self.NT)
+        assert isinstance(G_slots, np.ndarray) and G_slots.dtype == np.float64 and G_slots.shape == a.shape
+        self._check(self.lib.grape_b200_eval_fg_amplitudes(self._h, _dp(a), _dp(da), _dp(G_slots), _dp(self.J_parts),
+                                                           _dp(self.tau_vals.view(np.float64))))
+        self.fg_calls += 1
+        return float(np.sum(self.J_parts))
+
     # -- split form --------------------------------------------------------------
     def forward(self, pulsevals):
         x = self._pulses(pulsevals, self.L * self.NT)

@@ -54,6 +54,20 @@ class ShapedAmplitude:
         self.shape = shape
 
 
+class NonlinearAmplitude:
+    """a(t) = f(eps(t), t) with derivative df = d f / d eps -- a control that enters the generator non-linearly
+    (reference `get_control_derivs`, src/workspace.jl:283-285: mu = dH/d eps is then itself time dependent and is
+    evaluated per step, src/optimize.jl:946-951)."""
+
+    def __init__(self, control, func, dfunc):
+        self.control = control if isinstance(control, Control) else Control(control)
+        self.func, self.dfunc = func, dfunc
+
+
+def _control_of(c):
+    return c.control if isinstance(c, (ShapedAmplitude, NonlinearAmplitude)) else c
+
+
 class Generator:
     def __init__(self, H0, terms):
         self.H0 = np.asarray(H0, dtype=np.complex128)
@@ -64,7 +78,7 @@ def hamiltonian(H0, *terms):
     """`hamiltonian(H0, (H1, eps1), (H2, eps2), ...)` as in the reference README.md:40-44."""
     out = []
     for op, c in terms:
-        if not isinstance(c, (Control, ShapedAmplitude)):
+        if not isinstance(c, (Control, ShapedAmplitude, NonlinearAmplitude)):
             c = Control(c)
         out.append((np.asarray(op, dtype=np.complex128), c))
     return Generator(H0, out)
@@ -159,18 +173,94 @@ def get_controls(trajectories):
     controls = []
     for traj in trajectories:
         for _, c in traj.generator.terms:
-            ctrl = c.control if isinstance(c, ShapedAmplitude) else c
+            ctrl = _control_of(c)
             if not any(ctrl is x for x in controls):
                 controls.append(ctrl)
     return controls
 
 
+class AmplitudeSlots:
+    """Amplitude slots of a problem: one per distinct (control, amplitude) pair that occurs in the generators.
+
+    In the reference the amplitude (shape, non-linearity) belongs to each TERM of each generator.  The engine's
+    descriptor has L operator slots per generator; a slot is therefore (control, amplitude kind): 'lin' (a = eps),
+    ('shape', S) (a = S(t) eps) or ('nl', amplitude object) (a = f(eps, t)).  If every control has exactly one slot
+    and none is non-linear, the slots ARE the controls (`simple`): the engine differentiates with respect to the
+    pulse values directly (descriptor `shape`).  Otherwise the engine runs in amplitude mode: the host evaluates
+    a and da/d eps per slot and step and adds the slot gradients of each control (chain rule)."""
+
+    def __init__(self, controls, tlist):
+        from .configs import midpoints
+        self.controls, self.tm, self.NT = controls, midpoints(tlist), len(tlist) - 1
+        self.slots = []       # (control index, kind, payload)
+
+    def index_of(self, amp):
+        ctrl = _control_of(amp)
+        ci = next(i for i, x in enumerate(self.controls) if x is ctrl)
+        if isinstance(amp, ShapedAmplitude):
+            sv = np.vectorize(amp.shape, otypes=[float])(self.tm) if callable(amp.shape) else \
+                np.asarray(amp.shape, dtype=float) * np.ones(self.NT)
+            kind, payload = "shape", sv
+        elif isinstance(amp, NonlinearAmplitude):
+            kind, payload = "nl", amp
+        else:
+            kind, payload = "lin", None
+        for i, (c, k, pl) in enumerate(self.slots):
+            if c == ci and k == kind and (k == "lin" or (k == "shape" and np.array_equal(pl, payload)) or
+                                          (k == "nl" and pl is payload)):
+                return i
+        self.slots.append((ci, kind, payload))
+        return len(self.slots) - 1
+
+    @property
+    def simple(self):
+        cs = [c for c, _, _ in self.slots]
+        return all(k != "nl" for _, k, _ in self.slots) and sorted(cs) == list(range(len(self.controls)))
+
+    def control_order(self):
+        """permutation slot -> position such that slot i of the `simple` case is control i"""
+        return [next(i for i, (c, _, _) in enumerate(self.slots) if c == ci) for ci in range(len(self.controls))]
+
+    def shape_array(self):
+        """[L, NT] descriptor shape of the `simple` case (None if no control is shaped)"""
+        if all(k == "lin" for _, k, _ in self.slots):
+            return None
+        out = np.ones((len(self.controls), self.NT))
+        for c, k, pl in self.slots:
+            if k == "shape":
+                out[c] = pl
+        return out
+
+    def amplitudes(self, pulsevals):
+        """(ampl, dampl), each [n_slots * NT]: a_i(eps_c(i),n, t_n) and d a_i / d eps_c(i),n"""
+        eps = np.asarray(pulsevals, dtype=np.float64).reshape(len(self.controls), self.NT)
+        a = np.zeros((len(self.slots), self.NT))
+        da = np.zeros_like(a)
+        for i, (c, k, pl) in enumerate(self.slots):
+            if k == "lin":
+                a[i], da[i] = eps[c], 1.0
+            elif k == "shape":
+                a[i], da[i] = pl * eps[c], pl
+            else:
+                a[i] = [pl.func(e, t) for e, t in zip(eps[c], self.tm)]
+                da[i] = [pl.dfunc(e, t) for e, t in zip(eps[c], self.tm)]
+        return a.reshape(-1), da.reshape(-1)
+
+    def to_controls(self, G_slots):
+        """chain rule: dJ/d eps_c = sum of the slot gradients of control c"""
+        Gs = np.asarray(G_slots).reshape(len(self.slots), self.NT)
+        out = np.zeros((len(self.controls), self.NT))
+        for i, (c, _, _) in enumerate(self.slots):
+            out[c] += Gs[i]
+        return out.reshape(-1)
+
+
 def build_problem(trajectories, tlist, controls, functional, gradient_method=GRADGEN, ja_kind=JA_NONE,
                   lambda_a=1.0, g_b=None, lambda_b=1.0, **kw):
     """Flatten trajectories into the ABI descriptor's arrays; trajectories that share
-    a generator object share one device generator."""
+    a generator object share one device generator.  Returns (GrapeProblem, AmplitudeSlots)."""
     tlist = np.asarray(tlist, dtype=np.float64)
-    K, N, L, NT = len(trajectories), len(trajectories[0].initial_state), len(controls), len(tlist) - 1
+    K, N, NT = len(trajectories), len(trajectories[0].initial_state), len(tlist) - 1
     gens, gen_of = [], np.zeros(K, dtype=np.int32)
     for k, traj in enumerate(trajectories):
         for gi, g in enumerate(gens):
@@ -181,22 +271,24 @@ def build_problem(trajectories, tlist, controls, functional, gradient_method=GRA
             gens.append(traj.generator)
             gen_of[k] = len(gens) - 1
     G = len(gens)
+    slots = AmplitudeSlots(controls, tlist)
+    term_slot = [[slots.index_of(c) for _, c in g.terms] for g in gens]
+    if slots.simple:
+        order = slots.control_order()
+        pos = {s: i for i, s in enumerate(order)}
+        L = len(controls)
+        shape = slots.shape_array()
+    else:
+        pos = {i: i for i in range(len(slots.slots))}
+        L = len(slots.slots)
+        shape = None
+        ja_kind = JA_NONE       # J_a acts on the control values: evaluated on the host in amplitude mode
     H0 = np.zeros((G, N, N), dtype=np.complex128)
     Hc = np.zeros((G, L, N, N), dtype=np.complex128)
-    shape = None
-    from .configs import midpoints
-    tm = midpoints(tlist)
     for gi, g in enumerate(gens):
         H0[gi] = g.H0
-        for op, c in g.terms:
-            ctrl = c.control if isinstance(c, ShapedAmplitude) else c
-            l = next(i for i, x in enumerate(controls) if x is ctrl)
-            Hc[gi, l] += op
-            if isinstance(c, ShapedAmplitude):
-                if shape is None:
-                    shape = np.ones((L, NT))
-                s = c.shape
-                shape[l] = np.vectorize(s, otypes=[float])(tm) if callable(s) else np.asarray(s, dtype=float)
+        for (op, _), si in zip(g.terms, term_slot[gi]):
+            Hc[gi, pos[si]] += op
     psi0 = np.stack([t.initial_state for t in trajectories])
     tgt = np.stack([t.target_state if t.target_state is not None else np.zeros(N) for t in trajectories])
     w = np.array([t.weight for t in trajectories])
@@ -207,10 +299,11 @@ def build_problem(trajectories, tlist, controls, functional, gradient_method=GRA
                 "only the built-in quadratic form g_b runs on the device (arbitrary g_b/xi closures "
                 "would need every stored state on the host; DESIGN.md, out of scope)")
         gb_kind, D = GB_QUADFORM, g_b.D
-    return GrapeProblem(tlist, H0, Hc, psi0, tgt, gen_of_traj=gen_of, shape=shape,
+    prob = GrapeProblem(tlist, H0, Hc, psi0, tgt, gen_of_traj=gen_of, shape=shape,
                         weights=None if np.all(w == 1.0) else w, functional=functional,
                         gradient_method=gradient_method, ja_kind=ja_kind, lambda_a=lambda_a,
                         gb_kind=gb_kind, lambda_b=lambda_b, gb_D=D, **kw)
+    return prob, slots
 
 
 class GrapeWrk:
@@ -271,7 +364,7 @@ class GrapeWrk:
         gm = kw.get("gradient_method", "gradgen")
         if gm not in ("gradgen", "taylor"):
             raise ValueError(f"Invalid gradient_method={gm!r} ∉ (:gradgen, :taylor)")
-        self.problem = build_problem(
+        self.problem, self.slots = build_problem(
             trajectories, self.tlist, self.controls, functional,
             gradient_method=GRADGEN if gm == "gradgen" else TAYLOR, ja_kind=ja_kind,
             lambda_a=self.lambda_a, g_b=kw.get("g_b"), lambda_b=kw.get("lambda_b", 1.0),
@@ -280,6 +373,14 @@ class GrapeWrk:
             taylor_tolerance=kw.get("taylor_grad_tolerance", 1e-16),
             taylor_check_convergence=kw.get("taylor_grad_check_convergence", True),
             path=kw.get("path", PATH_AUTO))
+        self.amplitude_mode = not self.slots.simple
+        if self.amplitude_mode:
+            if functional == HOST:
+                raise NotImplementedError("a custom chi together with non-linear / per-term amplitudes is not supported")
+            if ja_kind == JA_FLUENCE:             # the device never sees the control values in amplitude mode
+                self.host_J_a = True
+                self.grad_J_a_func = lambda x, tl: (2.0 * np.asarray(x).reshape(-1, len(tl) - 1)
+                                                    * np.diff(tl)[None, :]).reshape(-1)
         if engine_factory is None:
             from .engine import GrapeEngine
             engine_factory = lambda prob: GrapeEngine(prob, device=kw.get("device", 0))
@@ -294,6 +395,9 @@ class GrapeWrk:
             self.J_parts[:] = 0.0
             self.J_parts[0] = self.J_T_func(list(states), self.trajectories)
             self.J_parts[2] = self.problem.lambda_b * e.sums[3] if self.problem.gb_kind else 0.0
+        elif self.amplitude_mode:
+            e.evaluate_functional_amplitudes(self.slots.amplitudes(pulsevals)[0])
+            self.J_parts[:] = e.J_parts
         else:
             e.evaluate_functional(pulsevals)
             self.J_parts[:] = e.J_parts
@@ -322,6 +426,16 @@ class GrapeWrk:
             if self.problem.ja_kind:
                 self.J_parts[1] = self.lambda_a * J_a_fluence(pulsevals, self.tlist)
                 G += self.lambda_a * self.grad_J_a
+        elif self.amplitude_mode:
+            # non-linear / per-term amplitudes: the host evaluates a and da/d eps per slot (get_control_derivs,
+            # src/workspace.jl:283-285; evaluate(mu), src/optimize.jl:946-951) and applies the chain rule
+            ampl, dampl = self.slots.amplitudes(pulsevals)
+            G_slots = np.zeros_like(ampl)
+            e.evaluate_gradient_amplitudes(G_slots, ampl, dampl)
+            self.J_parts[:] = e.J_parts
+            self.grad_J_Tb[:] = self.slots.to_controls(G_slots)
+            G[:] = self.grad_J_Tb
+            self.grad_J_a[:] = 0.0
         else:
             e.evaluate_gradient(G, pulsevals)
             self.J_parts[:] = e.J_parts

@@ -149,6 +149,21 @@ int grape_b200_eval_f(grape_b200_handle* h, const double* pulsevals,
 int grape_b200_eval_fg(grape_b200_handle* h, const double* pulsevals, double* G,
                        double* J_parts, double* tau, double* grad_J_Tb, double* grad_J_a);
 
+/* Amplitude mode: non-linear controls and per-term amplitudes.  The reference differentiates the generator with
+ * respect to each control through `get_control_derivs` (src/workspace.jl:283-285) and evaluates mu = dH/d eps per step
+ * when it is not a constant operator (src/optimize.jl:946-951; `isnothing(mu)` -> zero gradient).  Here the descriptor's
+ * L "controls" are amplitude SLOTS -- one per (control, amplitude) pair the generators contain -- and the host, which
+ * owns the closures, passes per call
+ *     ampl[i*NT + n]  = a_i(eps_{c(i),n}, t_n)             H_n = H0 + sum_i ampl[i][n] Hc_i
+ *     dampl[i*NT + n] = d a_i / d eps_{c(i),n}             mu_{i,n} = dampl[i][n] Hc_i   (0: no dependence)
+ * (L*NT scalar evaluations) and receives G_slots[i*NT + n] = dJ_T/d eps_{c(i),n} through slot i; it adds the slots of
+ * one control and J_a / grad_J_a itself (they act on the control values: create the handle with GRAPE_B200_JA_NONE).
+ * The descriptor's `shape` must be NULL for such a handle.  A linear control is the special case ampl = eps, dampl = 1,
+ * a ShapedAmplitude ampl = S eps, dampl = S. */
+int grape_b200_eval_f_amplitudes(grape_b200_handle* h, const double* ampl, double* J_parts, double* tau);
+int grape_b200_eval_fg_amplitudes(grape_b200_handle* h, const double* ampl, const double* dampl, double* G_slots,
+                                  double* J_parts, double* tau);
+
 /* Split form.  forward = src/optimize.jl:696-753 on the local shard.
  * sums[4] = local partial (Re sum_k w_k tau_k, Im sum_k w_k tau_k,
  *            sum_k w_k |tau_k|^2, sum_k J_b_trajectory[k]).

@@ -84,6 +84,9 @@ class OracleProblem:
         self.taylor_check_convergence = taylor_check_convergence
         # for a trajectory shard: the functionals are normalised by the GLOBAL K
         self.K_global = self.K if K_global is None else int(K_global)
+        # amplitude mode (non-linear controls, workspace.jl:283-285 / optimize.jl:946-951): when set, `pulsevals`
+        # holds the amplitudes a_{l,n} themselves and dampl[l,n] = d a_{l,n} / d eps scales the control derivative
+        self.dampl = None
 
 
 def from_problem(p, **overrides):
@@ -102,6 +105,8 @@ def from_problem(p, **overrides):
 # ----------------------------------------------------------------------------
 def amplitude(p, pulsevals, l, n):
     eps = pulsevals[l * p.NT + n]
+    if getattr(p, "dampl", None) is not None:
+        return eps
     return eps if p.shape is None else p.shape[l, n] * eps
 
 
@@ -116,6 +121,8 @@ def generator(p, pulsevals, k, n):
 def control_deriv(p, k, l, n):
     """mu_{k,l,n} = dH/d eps_{l,n}  (get_control_derivs, workspace.jl:283-285)."""
     g = p.gen_of_traj[k]
+    if getattr(p, "dampl", None) is not None:      # evaluate(mu) of a non-linear amplitude; 0: `isnothing(mu)` branch
+        return p.dampl[l, n] * p.Hc[g, l]
     s = 1.0 if p.shape is None else p.shape[l, n]
     return s * p.Hc[g, l]
 

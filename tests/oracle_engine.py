@@ -37,6 +37,21 @@ class OracleEngine:
     def final_states(self):
         return self._last["final_states"]
 
+    # amplitude mode (non-linear controls): pulsevals := amplitudes, control derivatives scaled by dampl
+    def evaluate_functional_amplitudes(self, ampl):
+        self.op.dampl = np.ones((self.L, self.NT))
+        try:
+            return self.evaluate_functional(ampl)
+        finally:
+            self.op.dampl = None
+
+    def evaluate_gradient_amplitudes(self, G_slots, ampl, dampl):
+        self.op.dampl = np.asarray(dampl, dtype=np.float64).reshape(self.L, self.NT)
+        try:
+            return self.evaluate_gradient(G_slots, ampl)
+        finally:
+            self.op.dampl = None
+
     # split protocol: emulate with the oracle's sigma_reduce hook
     def forward(self, x):
         self._x = np.array(x, dtype=np.float64)

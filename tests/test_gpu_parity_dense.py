@@ -29,7 +29,9 @@ def test_dense_readbacks_and_split(lib_built):
     sums = e.forward(eps)
     Gp = np.zeros_like(eps)
     e.backward(sums, Gp)
-    assert np.array_equal(Gp, G)
+    # eval_fg runs the two chains concurrently (chi_k(T) applied in the contraction), the split call one after the
+    # other: same series, different rounding
+    assert np.max(np.abs(Gp - G)) <= 1e-12 * np.max(np.abs(G))
 
 
 def test_c5_reduced_steps_full_width(lib_built):

@@ -149,7 +149,9 @@ def test_split_forward_backward_and_host_chi(lib_built):
     Gp = np.zeros_like(eps)
     e.backward(sums, Gp)
     assert e.gradient_form() >= 1
-    assert np.array_equal(Gp, G)
+    # eval_fg runs the two chains concurrently (chi_k(T) applied in the contraction), the split call one after the
+    # other: same series, different rounding
+    assert np.max(np.abs(Gp - G)) <= 1e-12 * np.max(np.abs(G))
     e.close()
     ph, _ = configs.c4_dense450(N=50, K=7, NT=5)
     ph.functional = gb.HOST
@@ -284,9 +286,9 @@ def test_concurrent_forward_and_backward_chains(lib_built, functional, terms):
             assert e.dense_concurrent() == conc and e.gradient_form() > 0
             assert abs(J - ref["J"]) <= 1e-10 and np.max(np.abs(e.tau_vals - ref["tau"])) <= 1e-10
             assert np.max(np.abs(G - ref["G"])) <= 1e-10 * scale
+            chi, rho = e.chi_states()
+            assert np.max(np.abs(chi - ref["chi_states"])) <= 1e-10 and np.max(np.abs(rho - ref["chi_norms"])) <= 1e-12
             assert abs(e.evaluate_functional(eps) - ref["J"]) <= 1e-10          # forward-only call in between
-        chi, rho = e.chi_states()
-        assert np.max(np.abs(chi - ref["chi_states"])) <= 1e-10 and np.max(np.abs(rho - ref["chi_norms"])) <= 1e-12
         # split host API: forward, then backward with the (here: local = global) sums -> sequential sweeps
         sums = e.forward(eps)
         Gp = np.zeros_like(eps)

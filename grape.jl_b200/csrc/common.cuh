@@ -52,6 +52,36 @@ GB_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memor
 template <int NPEND>
 GB_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND) : "memory"); }
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on a shared-memory mbarrier: one elected thread
+// hands whole rows to the copy engine instead of every thread issuing 16-byte LDGSTS.
+GB_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+GB_D void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// orders the mbarrier initialisation (generic proxy) before its use by the async proxy
+GB_D void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// generic-proxy accesses to shared memory (the warps' reads of the old tile) before async-proxy writes to it
+GB_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+GB_D void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned
+GB_D void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+GB_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // streaming (evict-first) 16-byte store for write-once storage
 GB_D void st_cs(cplx* p, cplx v) { __stcs(p, v); }
 GB_D cplx ld_cs(const cplx* p) { return __ldcs(p); }

@@ -116,6 +116,39 @@ J_T_re = _BuiltinJT(RE, "J_T_re")
 J_T_ss = _BuiltinJT(SS, "J_T_ss")
 
 
+# ---------------------------------------------------------------------------
+# gate functionals: J_T as a function of the achieved gate U_L in the logical subspace
+# (QuantumControl.Functionals.gate_functional / make_gate_chi; reference docs/src/background.md:552-610)
+# ---------------------------------------------------------------------------
+def logical_gate(states, basis):
+    """(U_L)_ij = <phi_i | Psi_j(T)>  (docs/src/background.md:556-562); one trajectory per logical basis state."""
+    Phi = np.asarray(basis, dtype=np.complex128)          # [d, N]
+    Psi = np.asarray(states, dtype=np.complex128)         # [d, N]
+    return Phi.conj() @ Psi.T
+
+
+def gate_functional(J_T_U, basis=None):
+    """`J_T(states, trajectories)` from a functional of the gate, `J_T_U(U_L)`.  `basis`: the logical basis states
+    (default: the trajectories' initial states, as the reference assumes)."""
+    def J_T(states, trajectories, tau=None):
+        B = [t.initial_state for t in trajectories] if basis is None else basis
+        return float(J_T_U(logical_gate(states, B)))
+    J_T.__name__ = getattr(J_T_U, "__name__", "J_T_U") + "_gate"
+    return J_T
+
+
+def make_gate_chi(grad_J_T_U, basis=None):
+    """`chi(states, trajectories)` for a gate functional from its gradient `grad_J_T_U(U_L)` = nabla_U J_T
+    (= 2 dJ_T/dU*, the reference's complex-gradient convention):
+        |chi_k(T)> = -1/2 sum_i (nabla_U J_T)_ik |phi_i>        (docs/src/background.md:600-606)
+    The reference obtains nabla_U J_T by automatic differentiation (make_gate_chi); here it is supplied."""
+    def chi(states, trajectories, tau=None):
+        B = np.asarray([t.initial_state for t in trajectories] if basis is None else basis, dtype=np.complex128)
+        g = np.asarray(grad_J_T_U(logical_gate(states, B)), dtype=np.complex128)   # [d, d], index (i, k)
+        return -0.5 * (g.T @ B)                                                    # row k = sum_i g[i, k] phi_i
+    return chi
+
+
 def J_a_fluence(pulsevals, tlist):
     dt = np.diff(tlist)
     e = np.asarray(pulsevals).reshape(-1, len(dt))

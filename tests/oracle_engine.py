@@ -55,13 +55,22 @@ class OracleEngine:
     # split protocol: emulate with the oracle's sigma_reduce hook
     def forward(self, x):
         self._x = np.array(x, dtype=np.float64)
-        r = go.evaluate_functional(self.op, x, sigma_reduce=lambda v: v)
+        r = go.evaluate_functional(self.op, x, sigma_reduce=lambda v: v,
+                                   jt_host=(lambda fs: 0.0) if self.op.functional == go.HOST else None)
         self._last = r
         w = self.op.weights
         self.tau_vals[:] = r["tau"]
         s = np.sum(w * r["tau"])
         self.sums[:] = [s.real, s.imag, np.sum(w * np.abs(r["tau"]) ** 2), np.sum(r["J_b_trajectory"])]
         return self.sums.copy()
+
+    def backward_chi(self, chiT, G_partial):
+        """host functional: chi_k(T) supplied by the caller (GrapeEngine.backward_chi)"""
+        chi = np.asarray(chiT, dtype=np.complex128)
+        r = go.evaluate_gradient(self.op, self._x, jt_host=lambda fs: 0.0, chi_host=lambda fs: chi)
+        G_partial[:] = r["grad_J_Tb"]
+        self.grad_J_a[:] = r["grad_J_a"]
+        return float(np.sum(r["J_b_trajectory"]))
 
     def backward(self, sums_global, G_partial):
         sig = complex(sums_global[0], sums_global[1])

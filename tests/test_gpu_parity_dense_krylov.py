@@ -328,3 +328,23 @@ def test_concurrent_chains_not_used_with_state_running_cost_or_host_chi(lib_buil
     assert e.dense_concurrent() == 0
     assert np.max(np.abs(Gp - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
     e.close()
+
+
+@pytest.mark.parametrize("conc", [1, 0])
+def test_tma_strip_prefetch_matches_cp_async(lib_built, conc):
+    """operator strips of the multi-term chains through the TMA copy engine (cp.async.bulk + mbarrier, default) or the
+    per-thread cp.async path (GRAPE_B200_DENSE_TMA=0): bit-identical gradients, both at 1e-10 of the oracle"""
+    p, eps = configs.c4_dense450(N=96, K=16, NT=11)
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    out = []
+    for tma in (1, 0):
+        with _Env(GRAPE_B200_DENSE2=0, GRAPE_B200_DENSE_TMA=tma, GRAPE_B200_DENSE_CONCURRENT=conc):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        for _ in range(2):
+            J = e.evaluate_gradient(G, eps)
+        assert e.gradient_form() == 2 and e.dense_concurrent() == conc
+        assert abs(J - ref["J"]) <= 1e-10 and np.max(np.abs(G - ref["G"])) <= 1e-10 * np.max(np.abs(ref["G"]))
+        out.append(G.copy())
+        e.close()
+    assert np.array_equal(out[0], out[1])

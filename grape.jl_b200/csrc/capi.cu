@@ -69,6 +69,7 @@ struct grape_b200_handle_impl {
     bool seg_fuse;        // small path, segmented: fused propagator formation + segment product (small_formseg)
     bool seg_scan;        // small path, real-symmetric generators: prefix products by a parallel scan, no boundary chains
     bool bounds_done;     // scan schedule: the segment boundaries of fw_storage hold the states of the current pulses
+    bool defer_tau;       // this gradient call forms the tau sums in the finalize kernel (uncoupled functional, one device)
     bool chain_dual;      // chain schedule: the forward phase of this call carried the targets backwards too (small_segchain_dual)
     bool chib_done;       // scan schedule: chiE / rho / chiT were written by small_scan_bounds for the current backward call
     int sym_v;            // 2: operators staged in shared memory (small_*_sym2, default); 1: round-1 kernels (GRAPE_B200_SYM_V=1)
@@ -143,6 +144,9 @@ int small_set_attrs(H* h) {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(h, cudaFuncSetAttribute(small_backward<N, SMALL_D>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (N <= 3)
+        CUDA_TRY(h, cudaFuncSetAttribute(small_segchain_dual<(N <= 3 ? N : 1)>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_ring_bytes(N)));
     return 0;
 }
 
@@ -436,7 +440,7 @@ void seg_chain_fwd_t(H* h) {
 }
 template <int N>
 void seg_chain_dual_t(H* h) {
-    small_segchain_dual<N><<<(h->p.K + 63) / 64, 64, 0, h->stream>>>(h->p, h->seg);
+    small_segchain_dual<N><<<(h->p.K + CHAIN_BD - 1) / CHAIN_BD, CHAIN_BD, chain_ring_bytes(N), h->stream>>>(h->p, h->seg);
     h->launches++;
 }
 template <int N>
@@ -561,14 +565,8 @@ void run_fill_interior(H* h) {
     }
 }
 bool xchg_live(const H* h) { return h->xchg_on && h->xchg_mode; }
-// first kernel of a sharded evaluation: the epochs of its exchanges (device-side, so that a captured graph replays)
-void run_xchg_begin(H* h, bool grad) {
-    h->xchg_fonly = !grad;
-    if (!xchg_live(h)) return;
-    const int bump0 = (!grad || h->p.functional == GRAPE_B200_JT_SM) ? 1 : 0;
-    xchg_begin<<<1, 1, 0, h->stream>>>(h->xd, bump0, grad ? 1 : 0);
-    h->launches++;
-}
+// start of an evaluation: remember whether it is a functional-only call (its sums are always exchanged)
+void run_xchg_begin(H* h, bool grad) { h->xchg_fonly = !grad; }
 void run_forward(H* h, bool need_storage = true, bool with_backward = false) {
     switch (h->path) {
         case GRAPE_B200_PATH_SMALL:
@@ -606,7 +604,10 @@ void run_forward(H* h, bool need_storage = true, bool with_backward = false) {
             else dense_run_forward(h->dense, h->p, h->stream, h->launches, with_backward);
             break;
     }
-    if (!(h->path == GRAPE_B200_PATH_SMALL && h->seg_on && h->seg_scan)) {   // (the scan schedule's tau kernel has done it)
+    // J_T_re / J_T_ss on one device: chi_k only needs tau_k, the sums are formed by the finalize kernel (one launch less)
+    h->defer_tau = with_backward && h->p.functional != GRAPE_B200_JT_SM && h->p.functional != GRAPE_B200_JT_HOST &&
+                   h->p.gb_kind == 0;
+    if (!(h->path == GRAPE_B200_PATH_SMALL && h->seg_on && h->seg_scan) && !h->defer_tau) {   // (the scan schedule's tau kernel has done it)
         reduce_tau<<<1, h->p.K >= 2048 ? 1024 : 256, 0, h->stream>>>(h->p);   // single block, fixed order; wider for large ensembles
         h->launches++;
     }
@@ -680,17 +681,22 @@ void run_gradient(H* h) {
 void run_finalize(H* h, bool grad) {
     if (grad) {
         const int blocks = (h->LNT + 31) / 32;
-        if (xchg_live(h))   // k-reduction fused with the all-reduce over the peers' shards (NVLink stores, xchg.cuh)
+        if (xchg_live(h)) {  // k-reduction fused with the all-reduce over the peers' shards (NVLink stores, xchg.cuh)
             finalize_grad_xchg<<<blocks < XCHG_MAXB ? blocks : XCHG_MAXB, 256, 0, h->stream>>>(
-                h->p, h->xd, h->p.functional != GRAPE_B200_JT_SM ? 1 : 0);
-        else
-            finalize_grad<<<blocks < 592 ? blocks : 592, 256, 0, h->stream>>>(h->p);
-        h->launches++;
+                h->p, h->xd, h->p.functional != GRAPE_B200_JT_SM ? 1 : 0, h->defer_tau ? 1 : 0);
+            h->launches++;
+            h->defer_tau = false;
+            return;
+        } else {             // k-reduction, J_a gradient and (last block) J_parts in one launch
+            finalize_grad<<<blocks < 592 ? blocks : 592, 256, 0, h->stream>>>(h->p, 1, h->defer_tau ? 1 : 0);
+            h->launches++;
+            h->defer_tau = false;
+            return;
+        }
     }
-    finalize_J<<<1, 256, 0, h->stream>>>(h->p);
+    finalize_J<<<1, 256, 0, h->stream>>>(h->p, 0);
     h->launches++;
 }
-
 void rec(H* h, int i) {
     if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
 }
@@ -901,7 +907,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
     for (int i = 0; i < 8; ++i) { h->ev[i] = nullptr; h->timings[i] = 0.0; }
     h->profiling = false; h->forward_done = false; h->backward_done = false; h->taugrads_valid = false; h->launches = 0;
     h->seg_on = false; h->interior_done = false; memset(&h->seg, 0, sizeof h->seg);
-    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->seg_scan = false; h->bounds_done = false; h->chib_done = false; h->chain_dual = false; h->d_taugrads = nullptr; h->taugrads_valid = false;
+    h->seg_herm = false; h->U_valid = false; h->seg_real = false; h->seg_fuse = false; h->sym_occ = 3; h->sym_v = 2; h->seg_scan = false; h->bounds_done = false; h->chib_done = false; h->chain_dual = false; h->defer_tau = false; h->d_taugrads = nullptr; h->taugrads_valid = false;
     h->wseg_on = false; memset(&h->wseg, 0, sizeof h->wseg);
     memset(&h->xd, 0, sizeof h->xd); h->xchg_on = false; h->xchg_mode = false; h->xchg_fonly = false;
     h->xchg_buf = nullptr; h->xchg_bytes = 0; h->launched_via_graph = false; h->launch_l0 = 0;
@@ -1202,7 +1208,7 @@ int grape_b200_enqueue_combine(grape_b200_handle* h) {
     combine_grad<<<blocks < 296 ? blocks : 296, 256, 0, h->stream>>>(h->p);
     // J_parts again, from the sums as they are NOW: for functionals whose chi does not couple the trajectories
     // (J_T_re, J_T_ss) the caller may all-reduce sums[4] together with grad_J_Tb, i.e. after enqueue_backward
-    finalize_J<<<1, 256, 0, h->stream>>>(h->p);
+    finalize_J<<<1, 256, 0, h->stream>>>(h->p, 0);
     h->launches += 2;
     return 0;
 }
@@ -1452,6 +1458,7 @@ int xchg_init_impl(H* h, int rank, int world) {
     h->xchg_bytes = l.bytes;
     h->xd.rank = rank; h->xd.world = world; h->xd.XS = l.XS;
     h->xd.epoch = reinterpret_cast<unsigned long long*>(static_cast<char*>(h->xchg_buf) + l.epoch_off);
+    h->xd.ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(h->xchg_buf) + l.epoch_off + 64);
     h->xd.timeout = &h->p.flags->xchg_timeout;
     xchg_point(h, rank, h->xchg_buf);
     return 0;

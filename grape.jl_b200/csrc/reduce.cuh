@@ -49,9 +49,24 @@ __global__ void __launch_bounds__(1024) reduce_tau(DevP p) {
     }
 }
 
-// J_parts from the (global) sums; J_a fluence = sum eps^2 dt (single block)
-__global__ void __launch_bounds__(256) finalize_J(DevP p) {
-    __shared__ double s_buf[32];
+// J_parts from the (global) sums; J_a fluence = sum eps^2 dt.  One block of 256 threads.
+// do_tau: the sums of reduce_tau are formed here first (functionals whose chi does not need them before the backward
+// sweep: one launch less per gradient).
+GB_D void finalize_J_body(const DevP& p, int do_tau, double* s_buf /* [32 * 4] */) {
+    if (do_tau) {
+        double t4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+            const double w = p.w ? p.w[k] : 1.0;
+            const cplx t = p.tau[k];
+            t4[0] = fma(w, t.x, t4[0]);
+            t4[1] = fma(w, t.y, t4[1]);
+            t4[2] = fma(w, cnorm2(t), t4[2]);
+            t4[3] += p.jb[k];
+        }
+        block_sum<4>(t4, s_buf);
+        if (threadIdx.x == 0) { p.sums[0] = t4[0]; p.sums[1] = t4[1]; p.sums[2] = t4[2]; p.sums[3] = t4[3]; }
+        __syncthreads();
+    }
     double v[1] = {0.0};
     if (p.ja_kind == 1) {
         for (int idx = threadIdx.x; idx < p.L * p.NT; idx += blockDim.x) {
@@ -75,13 +90,19 @@ __global__ void __launch_bounds__(256) finalize_J(DevP p) {
         p.Jparts[2] = p.gb_kind ? p.lambda_b * p.sums[3] : 0.0;
     }
 }
+__global__ void __launch_bounds__(256) finalize_J(DevP p, int do_tau) {
+    __shared__ double s_buf[32 * 4];
+    finalize_J_body(p, do_tau, s_buf);
+}
 
 // grad_J_Tb[idx] = -2 * sum_kb partial[kb][idx]   (optimize.jl:574-584)
 // grad_J_a[idx]  = 2 eps dt (fluence) ; G = grad_J_Tb + lambda_a grad_J_a  (optimize.jl:1003-1011)
 // A block sums 32 gradient elements: warp w takes the slabs kb = w, w + 8, .. (coalesced over idx, the loads of a
 // warp are independent), the eight partial sums meet in shared memory in fixed order (deterministic run to run).
-__global__ void __launch_bounds__(256) finalize_grad(DevP p) {
+// with_J: the last block also does finalize_J's work (one launch less; its J only needs tau / the sums, not the gradient)
+__global__ void __launch_bounds__(256) finalize_grad(DevP p, int with_J, int do_tau) {
     __shared__ double s_part[8][32];
+    __shared__ double s_bufJ[32 * 4];
     const int LNT = p.L * p.NT;
     const int KB = p.KBdev ? *p.KBdev : p.KB;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -110,4 +131,5 @@ __global__ void __launch_bounds__(256) finalize_grad(DevP p) {
         }
         __syncthreads();
     }
+    if (with_J && blockIdx.x == gridDim.x - 1) finalize_J_body(p, do_tau, s_bufJ);
 }

@@ -20,6 +20,8 @@
 // can be at most one exchange ahead (it cannot pass the next wait without our stamp).
 //
 //   channel 0: the 4 partial sums after the forward sweep (J_T_sm: chi_k needs sum_j tau_j)
+//   Epochs are device-side and self-incrementing: an exchange kernel works on (completed epochs + 1) and its last block
+//   to finish publishes the new count, so a captured CUDA graph replays and no extra kernel is needed.
 //   channel 1: the L*NT partial gradient (+ the 4 sums for J_T_re / J_T_ss, whose chi_k only
 //              needs tau_k) fused into finalize_grad
 #pragma once
@@ -32,7 +34,9 @@ constexpr int XCHG_MAXB = 296;    // pushing blocks per kernel (2 per SM: all co
 struct XchgDev {
     int rank, world;
     int XS;                               // doubles per slot (>= L*NT + 4, multiple of 2)
-    unsigned long long* epoch;            // [2] device-side call counters (channel 0 / 1), bumped by xchg_begin
+    unsigned long long* epoch;            // [2] device-side counters of COMPLETED exchanges (channel 0 / 1): an exchange kernel
+                                          // works on epoch + 1 and its last block to finish stores the new value
+    unsigned int* ticket;                 // [2] block-completion tickets of the exchange kernels (left at 0)
     double* slots[XCHG_MAXW];             // base of peer r's slot array   [2 ch][2 parity][world][XS]
     unsigned long long* flags[XCHG_MAXW]; // base of peer r's flag array   [2 ch][world][XCHG_MAXB]
     int* timeout;                         // [1] set when a wait gave up (peer never arrived)
@@ -63,10 +67,16 @@ GB_D unsigned long long globaltimer_ns() {
     return t;
 }
 
-// one thread, once per evaluation: the epochs of this call
-__global__ void xchg_begin(XchgDev x, int bump0, int bump1) {
-    if (bump0) x.epoch[0] += 1;
-    if (bump1) x.epoch[1] += 1;
+// called by every block when it is done with the exchange: the last one publishes the new epoch for the next launch
+GB_D void xchg_finish(const XchgDev& x, int ch, unsigned long long ep) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(&x.ticket[ch], 1u) == gridDim.x - 1) {
+            x.ticket[ch] = 0;
+            x.epoch[ch] = ep;
+            __threadfence();
+        }
+    }
 }
 
 // all stores of this block to the peers are done (every thread fenced): stamp + wait
@@ -92,7 +102,7 @@ GB_D void xchg_stamp_and_wait(const XchgDev& x, int ch, unsigned long long ep) {
 
 // channel 0: sums[4] <- sum over ranks, in rank order (single block)
 __global__ void __launch_bounds__(32) xchg_sums(DevP p, XchgDev x) {
-    const unsigned long long ep = x.epoch[0];
+    const unsigned long long ep = x.epoch[0] + 1;
     const int par = (int)(ep & 1), t = threadIdx.x;
     if (t < 4) {
         const double v = p.sums[t];
@@ -105,15 +115,18 @@ __global__ void __launch_bounds__(32) xchg_sums(DevP p, XchgDev x) {
         for (int r = 0; r < x.world; ++r) s += ld_volatile(mine + xchg_slot_off(x, 0, par, r) + t);
         p.sums[t] = s;
     }
+    xchg_finish(x, 0, ep);
 }
 
 // channel 1, fused with finalize_grad (reduce.cuh): grad_J_Tb = -2 sum_ranks sum_kb partial[kb],
 // grad_J_a = 2 eps dt, G = grad_J_Tb + lambda_a grad_J_a (optimize.jl:574-584, 1002-1011);
-// with_sums: block 0 also exchanges sums[4] (functionals whose chi does not couple the trajectories).
-// gridDim.x <= XCHG_MAXB; a block owns the 32-element chunks b, b + grid, ...
-__global__ void __launch_bounds__(256) finalize_grad_xchg(DevP p, XchgDev x, int with_sums) {
+// with_sums: block 0 also exchanges sums[4] (functionals whose chi does not couple the trajectories); do_tau: it forms
+// the local sums from tau first (no reduce_tau launch).  Block 0 finishes with J_parts from the global sums
+// (finalize_J's work).  gridDim.x <= XCHG_MAXB; a block owns the 32-element chunks b, b + grid, ...
+__global__ void __launch_bounds__(256) finalize_grad_xchg(DevP p, XchgDev x, int with_sums, int do_tau) {
     __shared__ double s_part[8][32];
-    const unsigned long long ep = x.epoch[1];
+    __shared__ double s_bufJ[32 * 4];
+    const unsigned long long ep = x.epoch[1] + 1;
     const int par = (int)(ep & 1);
     const int LNT = p.L * p.NT;
     const int KB = p.KBdev ? *p.KBdev : p.KB;
@@ -138,9 +151,25 @@ __global__ void __launch_bounds__(256) finalize_grad_xchg(DevP p, XchgDev x, int
         }
         __syncthreads();
     }
-    if (with_sums && blockIdx.x == 0 && threadIdx.x < 4) {
-        const double v = p.sums[threadIdx.x];
-        for (int r = 0; r < x.world; ++r) x.slots[r][my_slot + LNT + threadIdx.x] = v;
+    if (with_sums && blockIdx.x == 0) {
+        if (do_tau) {   // local sums of reduce_tau (same strided fixed-order accumulation)
+            double t4[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = threadIdx.x; k < p.K; k += blockDim.x) {
+                const double w = p.w ? p.w[k] : 1.0;
+                const cplx t = p.tau[k];
+                t4[0] = fma(w, t.x, t4[0]);
+                t4[1] = fma(w, t.y, t4[1]);
+                t4[2] = fma(w, cnorm2(t), t4[2]);
+                t4[3] += p.jb[k];
+            }
+            block_sum<4>(t4, s_bufJ);
+            if (threadIdx.x == 0) { p.sums[0] = t4[0]; p.sums[1] = t4[1]; p.sums[2] = t4[2]; p.sums[3] = t4[3]; }
+            __syncthreads();
+        }
+        if (threadIdx.x < 4) {
+            const double v = p.sums[threadIdx.x];
+            for (int r = 0; r < x.world; ++r) x.slots[r][my_slot + LNT + threadIdx.x] = v;
+        }
     }
     xchg_stamp_and_wait(x, 1, ep);
     const double* mine = x.slots[x.rank];
@@ -159,9 +188,14 @@ __global__ void __launch_bounds__(256) finalize_grad_xchg(DevP p, XchgDev x, int
             p.grad[2 * LNT + idx] = ga;
         }
     }
-    if (with_sums && blockIdx.x == 0 && threadIdx.x < 4) {
-        double s = 0.0;
-        for (int r = 0; r < x.world; ++r) s += ld_volatile(mine + xchg_slot_off(x, 1, par, r) + LNT + threadIdx.x);
-        p.sums[threadIdx.x] = s;
+    if (blockIdx.x == 0) {
+        if (with_sums && threadIdx.x < 4) {
+            double s = 0.0;
+            for (int r = 0; r < x.world; ++r) s += ld_volatile(mine + xchg_slot_off(x, 1, par, r) + LNT + threadIdx.x);
+            p.sums[threadIdx.x] = s;
+        }
+        __syncthreads();
+        finalize_J_body(p, 0, s_bufJ);   // J_parts from the global sums (finalize_J's work, no extra launch)
     }
+    xchg_finish(x, 1, ep);
 }

@@ -49,9 +49,10 @@ def _check_multi(p, eps, devices):
     assert abs(J - ref["J"]) <= 1e-12
     assert np.max(np.abs(m.J_parts - ref["J_parts"])) <= 1e-12
     assert np.max(np.abs(G - ref["G"])) <= 1e-12 * sc
-    assert np.array_equal(m.tau_vals, ref["tau"])                  # per-trajectory work is unchanged by the split
+    # per-trajectory work is unchanged by the split up to the schedule the shard size selects (segment length, scan)
+    assert np.max(np.abs(m.tau_vals - ref["tau"])) <= 1e-13
     assert abs(m.evaluate_functional(eps) - ref["Jf"]) <= 1e-12
-    assert np.array_equal(m.final_states(), ref["fs"])
+    assert np.max(np.abs(m.final_states() - ref["fs"])) <= 1e-13
     for _ in range(3):                                             # fixed-order reductions: bit-identical run to run
         G2 = np.zeros_like(eps)
         J2 = m.evaluate_gradient(G2, eps)

@@ -81,11 +81,12 @@ GB_D void xchg_finish(const XchgDev& x, int ch, unsigned long long ep) {
 
 // all stores of this block to the peers are done (every thread fenced): stamp + wait
 GB_D void xchg_stamp_and_wait(const XchgDev& x, int ch, unsigned long long ep) {
-    __threadfence_system();
+    // The block's peer stores happen-before the barrier; the system-scope RELEASE store of the stamping thread is
+    // cumulative over everything ordered before it through the barrier, so one release per peer suffices (a
+    // __threadfence_system() by each of the 256 threads cost several NVLink round trips per exchange).
     __syncthreads();
     const int t = threadIdx.x;
     if (t < x.world) {
-        __threadfence_system();
         st_release_sys(x.flags[t] + xchg_flag_off(x, ch, x.rank, blockIdx.x), ep);   // my stamp on peer t
         const unsigned long long* f = x.flags[x.rank] + xchg_flag_off(x, ch, t, blockIdx.x);
         const unsigned long long t0 = globaltimer_ns();

@@ -717,6 +717,10 @@ void collect_timings(H* h, int64_t launches_before) {
 int check_flags(H* h) {
     const DevFlags* f = reinterpret_cast<const DevFlags*>(h->h_out + h->off_flags);
     char b[256];
+    if (f->xchg_timeout == 2) {
+        h->err = "internal error: a split-phase barrier of the concurrent dense chains timed out";
+        return GRAPE_B200_ECUDA;
+    }
     if (f->xchg_timeout) {
         h->err = "peer exchange timed out: a shard of this trajectory-sharded problem did not reach the exchange "
                  "(every rank must make the same sequence of evaluation calls)";

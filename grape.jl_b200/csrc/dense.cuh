@@ -57,6 +57,8 @@ struct KryDev {
     int conc;          // concurrent forward / backward chains (dense_chain<2, NS>): the chi chain propagates tgt_k / ||tgt_k||
     double* kfac;      // [2][Kp] (re, im) ||tgt_k|| conj(c_k): factor of e_b in kry_combine instead of rho_k
     const double* tgtn;// [2][Np][Kp] planar tgt_k / ||tgt_k||: start of the concurrent chi chain
+    unsigned* bars;    // [2 directions][Kp / 8 column groups][32] arrival counters of the split-phase barriers (one 128-byte
+                       // line each; zeroed before every concurrent launch)
 };
 
 struct DenseDev {
@@ -473,6 +475,29 @@ GB_D void dense_prefetch_strips(const double* __restrict__ pre, int n, int Np, i
     cp_async_commit();
 }
 
+// Split-phase barrier of one (direction, 8-column group): the Taylor terms of a column group only depend on the SAME
+// group's previous term on all row tiles, so every group gets its own arrival counter.  A CTA that owns two groups
+// arrives for group A, computes group B, and only then waits for A: the barrier round trip and the arrival skew of
+// the other CTAs are hidden behind DMMA work instead of being paid per stage (cooperative_groups' grid.sync() of the
+// whole grid cost ~40 % of the chain).  All CTAs are co-resident (cooperative launch), so spinning is safe; a wait
+// gives up after ~10 s and flags the call instead of hanging the GPU.
+GB_D unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+GB_D void split_arrive(unsigned* bar) {   // call after __syncthreads(), by one thread
+    __threadfence();
+    atomicAdd(bar, 1u);
+}
+GB_D void split_wait(const unsigned* bar, unsigned target, DevFlags* flags) {   // by one thread, then __syncthreads()
+    if (ld_acquire_gpu_u32(bar) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu_u32(bar) < target) {
+        if (clock64() - t0 > 20000000000ll) { flags->xchg_timeout = 2; break; }
+    }
+}
+
 // The same strips through the TMA copy engine: thread 0 arms the mbarrier with the byte count and issues one bulk copy
 // per (plane, row) -- 2 NS x 8 rows of Np doubles, 184 KB per step for C4 -- instead of 45 LDGSTS per thread.
 template <int NS>
@@ -545,6 +570,9 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
     double* coef = jb_s + Ccap + 8;                 // NS >= 2: pair coefficients c_i c_j of the current step (<= 64)
     double* HX = coef + 64;                         // NS >= 2: rows of H_n^2 [, H_n^3], 16 MS doubles each
     constexpr bool DUAL = NS >= 2;
+    constexpr bool SPLIT = MODE == 2 && NS >= 2;   // per-(direction, column group) split-phase barriers instead of grid.sync()
+    unsigned* const mybars = SPLIT ? kd.bars + (size_t)(BWD ? 1 : 0) * (Kp / 8) * 32 : nullptr;
+    unsigned round = 0;                            // arrivals this CTA has made per column group
     auto stages_of = [&](int mm) { return DUAL ? (mm + NS - 1) / NS : mm; };   // grid barriers of a Krylov-form step
     const double* const Bq[3] = {Hs_re, HX, HX + 16 * MS};
     const size_t splane = (size_t)Np * Kp;
@@ -669,6 +697,11 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                     for (int pg = cg0; pg < cg1; pg += pgstep) {
                         const int ng = min(pgstep, cg1 - pg);
                         const int g = threadIdx.x >> 6, idx = threadIdx.x & 63, nrow = idx >> 3, mc = idx & 7;
+                        if (SPLIT) {   // the operand columns of these groups are complete on every row tile
+                            if (threadIdx.x == 0)
+                                for (int gg = 0; gg < ng; ++gg) split_wait(mybars + (size_t)(pg + gg) * 32, round * (unsigned)d.RT, p.flags);
+                            __syncthreads();
+                        }
                         if (nt == NS) {
                             DAcc acc[NS];
 #pragma unroll
@@ -694,6 +727,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                                 }
                                 acc_re[nrow * Ccap + cglob - cbeg] = ar;
                                 acc_im[nrow * Ccap + cglob - cbeg] = ai;
+                            }
+                            if (SPLIT && j + NS < m) {   // this group's new terms are written: arrive, go on with the next group
+                                __syncthreads();
+                                if (threadIdx.x == 0) split_arrive(mybars + (size_t)pg * 32);
                             }
                         } else {
                             // several column groups per CTA (or a short last stage): one pass per strip
@@ -722,7 +759,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                             }
                         }
                     }
-                    if (j + NS < m) grid.sync();
+                    if (SPLIT) { if (j + NS < m) ++round; }
+                    else if (j + NS < m) grid.sync();
                 }
             } else
             for (int j = 1; j <= m; ++j) {
@@ -793,6 +831,17 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                 }
                 __syncthreads();
             }
+            if (SPLIT && stages_of(m) == 1) {
+                // a one-stage step has no barrier between reading `state` (the operand of its only stage) and overwriting
+                // it below: one extra round so that every row tile is done reading
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int pg = cg0; pg < cg1; ++pg) split_arrive(mybars + (size_t)pg * 32);
+                ++round;
+                if (threadIdx.x == 0)
+                    for (int pg = cg0; pg < cg1; ++pg) split_wait(mybars + (size_t)pg * 32, round * (unsigned)d.RT, p.flags);
+                __syncthreads();
+            }
             for (int e = threadIdx.x; e < 8 * ncols; e += DENSE_THREADS) {
                 const int r = e / ncols, c = e % ncols;
                 const size_t off = (size_t)(r0 + r) * Kp + cbeg + c;
@@ -811,9 +860,14 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                     }
                 }
             }
-            grid.sync();
+            if (SPLIT) {   // the new state of every column group of this CTA is written
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int pg = cg0; pg < cg1; ++pg) split_arrive(mybars + (size_t)pg * 32);
+                ++round;
+            } else grid.sync();
         }
-        if (MODE == 2) {   // both directions make the same number of grid barriers per iteration (uniform per role)
+        if (MODE == 2 && !SPLIT) {   // both directions make the same number of grid barriers per iteration (uniform per role)
             const int mo = kd.m_n[BWD ? it : NT - 1 - it];
             for (int x = stages_of(m); x < stages_of(mo); ++x) grid.sync();
         }
@@ -1446,6 +1500,9 @@ inline int dense_concurrent_setup(DensePlan& dp, const DevP& p, const double* tg
     allocs.push_back(q);
     cudaMemset(q, 0, 2 * (size_t)d.Kp * sizeof(double));
     dp.kd.kfac = static_cast<double*>(q);
+    if (cudaMalloc(&q, 2 * (size_t)(d.Kp / 8) * 32 * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return 0; }
+    allocs.push_back(q);
+    dp.kd.bars = static_cast<unsigned*>(q);
     dp.dD = dd;
     dp.gridD = 2 * d.RT * dd.Pf;
     dp.smemD = smem;
@@ -1496,6 +1553,7 @@ inline void dense_run_forward(DensePlan& dp, const DevP& p, cudaStream_t st, int
         // Krylov form; then the forward-only kernel below does the sweep as before)
         if (d.nstrip > 1 && d.preA && d.preA != d.preF) dense_run_preform(dp, p, true, st, launches);
         cudaMemcpyAsync(dp.kd.kcur, dp.kd.tgtn, 2 * splane * sizeof(double), cudaMemcpyDeviceToDevice, st);
+        cudaMemsetAsync(dp.kd.bars, 0, 2 * (size_t)(d.Kp / 8) * 32 * sizeof(unsigned), st);
         void* dargs[] = {&pp, &dp.dD, &dp.kd, &skip};
         dense_chain_launch<2>(dp, dargs, st);
         launches++;

@@ -310,6 +310,9 @@ int small_setup(H* h, const grape_b200_problem* d) {
         // the scan schedule below runs one block of up to 128 segment threads per generator: worthwhile from 64 generators
         // on (a 512-trajectory shard of the C3 ensemble on 8 GPUs must not drop to the unfused kernels)
         if (h->seg_real && h->sym_v != 1 && G >= 64 && NT >= 64) h->seg_fuse = true;
+        // ... and small ensembles down to the single README trajectory (C1): formation + scan, tau, gradient, finalize
+        // are 4 short kernels in one CUDA graph instead of 9 (per-step formation, segment products, two chains, ...)
+        if (h->seg_real && h->sym_v != 1 && K <= 2048 && NT >= 8) h->seg_fuse = true;
         if (getenv("GRAPE_B200_FORCE_FORMSEG") && atoi(getenv("GRAPE_B200_FORCE_FORMSEG")) != 0) h->seg_fuse = true;
         if (getenv("GRAPE_B200_NO_FORMSEG")) h->seg_fuse = false;
         // real-symmetric generators, fused formation: prefix products by a parallel scan inside the formation kernel
@@ -325,7 +328,9 @@ int small_setup(H* h, const grape_b200_problem* d) {
             h->seg_scan = h->seg_real && h->sym_v != 1 && h->seg_fuse && L <= 16 && atoi(e) != 0;
         if (h->seg_scan) {
             const long long KGR = (K + a.BKL - 1) / a.BKL;
-            const int target = KGR >= 64 ? 64 : 96;     // segments per generator: measured optimum 63 (K = 2048), 91 (K <= 1024)
+            // segments per generator: measured optimum 63 (K = 2048), 91 (K <= 1024); a handful of trajectories: as many
+            // as one block holds (pure dependency latency, the shortest segments win)
+            const int target = KGR >= 64 ? 64 : (KGR >= 8 ? 96 : 128);
             S = (NT + target - 1) / target;
             if (S < 2) S = 2;
         }

@@ -375,6 +375,35 @@ GB_D double sym_form_H_staged(const DevP& p, const double* sH, int L, int n, dou
     return nrm;
 }
 
+// cos(Hs) and Sp = sin(Hs)/Hs as Horner polynomials in Q = Hs^2 with D2 + 1 terms each; D2 is a template parameter
+// (the four degree classes of exp_plan: 3, 7, 11, 15 -> D2 = 1, 3, 5, 7), so the coefficients are immediates and the
+// loop unrolls (the run-time loop cost 15 % of the formation kernel's instructions in IMAD / LDC / branches)
+template <int N, int D2>
+GB_D void sym_cos_sinc_poly(const double (&Q)[N * N], double (&Cm)[N * N], double (&Sp)[N * N]) {
+    constexpr int NN = N * N;
+    {
+        constexpr double sg = (D2 & 1) ? -1.0 : 1.0;
+        const double c1 = sg * c_invfact[2 * D2], c0 = -sg * c_invfact[2 * D2 - 2];
+        const double s1 = sg * c_invfact[2 * D2 + 1], s0 = -sg * c_invfact[2 * D2 - 1];
+#pragma unroll
+        for (int c = 0; c < NN; ++c) { Cm[c] = c1 * Q[c]; Sp[c] = s1 * Q[c]; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Cm[i * N + i] += c0; Sp[i * N + i] += s0; }
+    }
+#pragma unroll
+    for (int j = D2 - 2; j >= 0; --j) {
+        const double sg = (j & 1) ? -1.0 : 1.0;
+        const double cj = sg * c_invfact[2 * j], sj = sg * c_invfact[2 * j + 1];
+        double T1[NN], T2[NN];
+        rm_mm<N>(T1, Q, Cm);
+        rm_mm<N>(T2, Q, Sp);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) { Cm[c] = T1[c]; Sp[c] = T2[c]; }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { Cm[i * N + i] += cj; Sp[i * N + i] += sj; }
+    }
+}
+
 // U_n = cos(Hs) - i sin(Hs) of one step (Hs unscaled generator, theta = dt * ||Hs||_1), as in small_formseg_sym
 template <int N>
 GB_D void sym_cos_sin(double (&Hs)[N * N], double dt, double theta, double (&Cm)[N * N], double (&Sm)[N * N]) {
@@ -386,27 +415,12 @@ GB_D void sym_cos_sin(double (&Hs)[N * N], double dt, double theta, double (&Cm)
     for (int c = 0; c < NN; ++c) Hs[c] *= sc;
     double Q[NN];
     rm_mm<N>(Q, Hs, Hs);
-    const int d2 = (degree - 1) / 2;
     double Sp[NN];
-    {
-        const double sg = (d2 & 1) ? -1.0 : 1.0;
-        const double c1 = sg * c_invfact[2 * d2], c0 = -sg * c_invfact[2 * d2 - 2];
-        const double s1 = sg * c_invfact[2 * d2 + 1], s0 = -sg * c_invfact[2 * d2 - 1];
-#pragma unroll
-        for (int c = 0; c < NN; ++c) { Cm[c] = c1 * Q[c]; Sp[c] = s1 * Q[c]; }
-#pragma unroll
-        for (int i = 0; i < N; ++i) { Cm[i * N + i] += c0; Sp[i * N + i] += s0; }
-    }
-    for (int j = d2 - 2; j >= 0; --j) {
-        const double sg = (j & 1) ? -1.0 : 1.0;
-        const double cj = sg * c_invfact[2 * j], sj = sg * c_invfact[2 * j + 1];
-        double T1[NN], T2[NN];
-        rm_mm<N>(T1, Q, Cm);
-        rm_mm<N>(T2, Q, Sp);
-#pragma unroll
-        for (int c = 0; c < NN; ++c) { Cm[c] = T1[c]; Sp[c] = T2[c]; }
-#pragma unroll
-        for (int i = 0; i < N; ++i) { Cm[i * N + i] += cj; Sp[i * N + i] += sj; }
+    switch (degree) {   // same operations in the same order as the run-time Horner loop of small_formseg_sym
+        case 3: sym_cos_sinc_poly<N, 1>(Q, Cm, Sp); break;
+        case 7: sym_cos_sinc_poly<N, 3>(Q, Cm, Sp); break;
+        case 11: sym_cos_sinc_poly<N, 5>(Q, Cm, Sp); break;
+        default: sym_cos_sinc_poly<N, 7>(Q, Cm, Sp); break;
     }
     rm_mm<N>(Sm, Hs, Sp);
     for (int t = 0; t < s; ++t) {   // (C - iS)^2 = (C^2 - S^2) - i (2 S C)
@@ -650,22 +664,34 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs 
 #pragma unroll
             for (int i = 0; i < N; ++i) { psi[i] = psi2[i]; chi[i] = chi2[i]; }
         }
-        auto one_control = [&](int l) {
+        auto trace = [&](int l) {
             double sl = dt * rho;
             if (p.dshape) sl *= p.dshape[l * NT + nn];
             double acc = 0.0;
 #pragma unroll
             for (int c = 0; c < NN; ++c) acc = fma(sH[(NN + l * NN + c) * SYM_BD + threadIdx.x], IM[c], acc);
-            double red = act ? sl * acc : 0.0;
-            // fixed-order sum over the BKL trajectories of this lane group
-            for (int off = BKL >> 1; off > 0; off >>= 1) red += __shfl_down_sync(0xffffffffu, red, off, BKL);
-            if (writer && n >= n0) part[(size_t)l * NT + n] = red;
+            return act ? sl * acc : 0.0;
         };
         if (LT > 0) {
+            // the LT fixed-order sums over the BKL trajectories of this lane group run interleaved: one chain of
+            // dependent SHFL + DADD per control was the kernel's largest scoreboard stall
+            double red[LT > 0 ? LT : 1];
 #pragma unroll
-            for (int l = 0; l < LT; ++l) one_control(l);
+            for (int l = 0; l < LT; ++l) red[l] = trace(l);
+            for (int off = BKL >> 1; off > 0; off >>= 1) {
+#pragma unroll
+                for (int l = 0; l < LT; ++l) red[l] += __shfl_down_sync(0xffffffffu, red[l], off, BKL);
+            }
+            if (writer && n >= n0) {
+#pragma unroll
+                for (int l = 0; l < LT; ++l) part[(size_t)l * NT + n] = red[l];
+            }
         } else {
-            for (int l = 0; l < L; ++l) one_control(l);
+            for (int l = 0; l < L; ++l) {
+                double red = trace(l);
+                for (int off = BKL >> 1; off > 0; off >>= 1) red += __shfl_down_sync(0xffffffffu, red, off, BKL);
+                if (writer && n >= n0) part[(size_t)l * NT + n] = red;
+            }
         }
     }
 }

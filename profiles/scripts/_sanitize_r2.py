@@ -23,10 +23,10 @@ def run(p, eps, **env):
             os.environ.pop(k, None)
     G = np.zeros_like(eps)
     J = e.evaluate_gradient(G, eps)
-    e.evaluate_functional(eps)
-    e.stored_states(0)
     if p.N <= 32:
         e.tau_grads(0)
+    e.evaluate_functional(eps)
+    e.stored_states(0)
     J2 = e.evaluate_gradient(G, eps)
     assert J == J2
     e.close()

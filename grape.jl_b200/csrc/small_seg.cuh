@@ -316,16 +316,24 @@ __global__ void __launch_bounds__(CHAIN_BD) small_segchain_dual(DevP p, SegArgs 
     const bool live = k < K;
     const int g = p.gen[kk];
     const cplx* Pg = a.Pseg + g;
+    // running source pointers (one 64-bit add per element instead of a 64-bit multiply-add chain: with one warp per SM
+    // the kernel is bound by the latency of its ~250 mostly-integer instructions per segment, not by memory)
+    const cplx* pf = Pg;                                            // P of the segment the next issue() fetches, forward order
+    const cplx* pb = Pg + (size_t)(a.NSEG - 1) * NN * G;            // ... backward order
+    const size_t segstride = (size_t)NN * G;
     auto issue = [&](int s) {
         if (s < a.NSEG) {
             cplx* st = ring + (size_t)(s % CHAIN_D) * 2 * NN * CHAIN_BD + threadIdx.x;
-            const int sb = a.NSEG - 1 - s;
+            const cplx* q = pf;
 #pragma unroll
-            for (int c = 0; c < NN; ++c) cp_async16(st + c * CHAIN_BD, &Pg[((size_t)s * NN + c) * G]);
-            if (sb > 0) {
+            for (int c = 0; c < NN; ++c) { cp_async16(st + c * CHAIN_BD, q); q += G; }
+            if (s < a.NSEG - 1) {                                   // (segment 0 is never applied backwards)
+                q = pb;
 #pragma unroll
-                for (int c = 0; c < NN; ++c) cp_async16(st + (NN + c) * CHAIN_BD, &Pg[((size_t)sb * NN + c) * G]);
+                for (int c = 0; c < NN; ++c) { cp_async16(st + (NN + c) * CHAIN_BD, q); q += G; }
             }
+            pf += segstride;
+            pb -= segstride;
         }
         cp_async_commit();
     };
@@ -351,15 +359,20 @@ __global__ void __launch_bounds__(CHAIN_BD) small_segchain_dual(DevP p, SegArgs 
             nw[i] = acc;
         }
         const int nb = min(NT, (sf + 1) * a.S);
+        {
+            cplx* o = p.psi + (size_t)nb * N * K + k;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            psi[i] = nw[i];
-            if (live) st_cs(&p.psi[((size_t)nb * N + i) * K + k], psi[i]);
+            for (int i = 0; i < N; ++i) {
+                psi[i] = nw[i];
+                if (live) st_cs(o, psi[i]);
+                o += K;
+            }
         }
         // the target at the END of segment sb, then through P_sb^dagger
         if (live) {
+            cplx* o = a.chiE + (size_t)sb * N * K + k;
 #pragma unroll
-            for (int i = 0; i < N; ++i) a.chiE[((size_t)sb * N + i) * K + k] = y[i];
+            for (int i = 0; i < N; ++i) { *o = y[i]; o += K; }
         }
         if (sb > 0) {
             cplx ny[N];

@@ -269,7 +269,7 @@ def test_concurrent_forward_and_backward_chains(lib_built, functional, terms):
     grid, chi_k(T) = c_k tgt_k being applied afterwards in the contraction.  Against the oracle, against the sequential
     sweeps (GRAPE_B200_DENSE_CONCURRENT=0), with Taylor orders that differ between step n and step NT-1-n (pulse ramp:
     the two directions need different numbers of grid barriers per iteration), weights, and call after call."""
-    N, K, NT = 72, 16, 9
+    N, K, NT = 48, 16, 9
     w = np.linspace(0.5, 1.5, K)
     p, eps = configs.c4_dense450(N=N, K=K, NT=NT, functional=functional, weights=w)
     ramp = np.linspace(0.05, 2.5, NT)                      # ||H_n dt|| from ~0.1 to ~0.9: orders 9 .. 18

@@ -445,7 +445,7 @@ void seg_chain_fwd_t(H* h) {
 }
 template <int N>
 void seg_chain_dual_t(H* h) {
-    small_segchain_dual<N><<<(h->p.K + CHAIN_BD - 1) / CHAIN_BD, CHAIN_BD, chain_ring_bytes(N), h->stream>>>(h->p, h->seg);
+    small_segchain_dual<N><<<(h->p.K + CHAIN_BD - 1) / CHAIN_BD, 2 * CHAIN_BD, chain_ring_bytes(N), h->stream>>>(h->p, h->seg);
     h->launches++;
 }
 template <int N>

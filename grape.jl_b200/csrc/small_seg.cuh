@@ -303,97 +303,103 @@ __global__ void __launch_bounds__(64) small_segchain_bwd(DevP p, SegArgs a, cons
 // order) through a private column of a cp.async ring in shared memory, CHAIN_D - 1 segments ahead, so that a chain
 // step costs one dependent mat-vec instead of one L2 round trip (measured: 25 us -> see profiles/ for 45 segments).
 constexpr int CHAIN_D = 8;     // ring depth
-constexpr int CHAIN_BD = 32;   // threads per block (one warp: 128 blocks for 4096 trajectories)
-inline size_t chain_ring_bytes(int N) { return (size_t)CHAIN_D * 2 * N * N * CHAIN_BD * sizeof(cplx); }
+constexpr int CHAIN_BD = 32;   // trajectories per block; the block has 2 warps: warp 0 = forward chain, warp 1 = backward chain
+inline size_t chain_ring_bytes(int N) { return (size_t)2 * CHAIN_D * N * N * CHAIN_BD * sizeof(cplx); }
 
+// With one warp per SM the chain is bound by the issue latency of its own instruction stream (ncu: 0.26 IPC, 244
+// instructions per segment for both directions), so the two directions get a warp each: same 32 trajectories, half
+// the instructions per warp, no synchronisation between them.
 template <int N>
-__global__ void __launch_bounds__(CHAIN_BD) small_segchain_dual(DevP p, SegArgs a) {
+__global__ void __launch_bounds__(2 * CHAIN_BD) small_segchain_dual(DevP p, SegArgs a) {
     constexpr int NN = N * N;
-    extern __shared__ __align__(16) cplx ring[];   // [CHAIN_D][2 NN][CHAIN_BD]
+    extern __shared__ __align__(16) cplx ring_all[];   // [2 roles][CHAIN_D][NN][CHAIN_BD]
     const int K = p.K, G = p.G, NT = p.NT;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & (CHAIN_BD - 1);
+    const bool bwd = threadIdx.x >= CHAIN_BD;
+    cplx* ring = ring_all + (bwd ? (size_t)CHAIN_D * NN * CHAIN_BD : 0) + lane;
+    const int k = blockIdx.x * CHAIN_BD + lane;
     const int kk = k < K ? k : K - 1;              // idle lanes stream valid addresses and store nothing
     const bool live = k < K;
     const int g = p.gen[kk];
     const cplx* Pg = a.Pseg + g;
-    // running source pointers (one 64-bit add per element instead of a 64-bit multiply-add chain: with one warp per SM
-    // the kernel is bound by the latency of its ~250 mostly-integer instructions per segment, not by memory)
-    const cplx* pf = Pg;                                            // P of the segment the next issue() fetches, forward order
-    const cplx* pb = Pg + (size_t)(a.NSEG - 1) * NN * G;            // ... backward order
     const size_t segstride = (size_t)NN * G;
+    // running source pointer (one 64-bit add per element): forward role walks the segments upwards, backward role downwards
+    const cplx* src = bwd ? Pg + (size_t)(a.NSEG - 1) * segstride : Pg;
+    const int nuse = bwd ? a.NSEG - 1 : a.NSEG;    // the backward role never applies P of segment 0
     auto issue = [&](int s) {
-        if (s < a.NSEG) {
-            cplx* st = ring + (size_t)(s % CHAIN_D) * 2 * NN * CHAIN_BD + threadIdx.x;
-            const cplx* q = pf;
+        if (s < nuse) {
+            cplx* st = ring + (size_t)(s % CHAIN_D) * NN * CHAIN_BD;
+            const cplx* q = src;
 #pragma unroll
             for (int c = 0; c < NN; ++c) { cp_async16(st + c * CHAIN_BD, q); q += G; }
-            if (s < a.NSEG - 1) {                                   // (segment 0 is never applied backwards)
-                q = pb;
-#pragma unroll
-                for (int c = 0; c < NN; ++c) { cp_async16(st + (NN + c) * CHAIN_BD, q); q += G; }
-            }
-            pf += segstride;
-            pb -= segstride;
+            if (bwd) src -= segstride; else src += segstride;
         }
         cp_async_commit();
     };
 #pragma unroll
     for (int s = 0; s < CHAIN_D - 1; ++s) issue(s);
-    cplx psi[N], y[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        psi[i] = p.psi0[(size_t)i * K + kk];
-        if (live) st_cs(&p.psi[(size_t)i * K + k], psi[i]);
-        y[i] = p.tgt[(size_t)i * K + kk];
-    }
-    for (int sf = 0; sf < a.NSEG; ++sf) {
-        cp_async_wait<CHAIN_D - 2>();              // this thread's copies of segment sf have landed
-        const cplx* st = ring + (size_t)(sf % CHAIN_D) * 2 * NN * CHAIN_BD + threadIdx.x;
-        const int sb = a.NSEG - 1 - sf;
-        cplx nw[N];
+    cplx x[N];
+    if (!bwd) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            cplx acc = mk(0.0, 0.0);
-#pragma unroll
-            for (int j = 0; j < N; ++j) cfma(acc, st[(i * N + j) * CHAIN_BD], psi[j]);
-            nw[i] = acc;
+            x[i] = p.psi0[(size_t)i * K + kk];
+            if (live) st_cs(&p.psi[(size_t)i * K + k], x[i]);
         }
-        const int nb = min(NT, (sf + 1) * a.S);
-        {
-            cplx* o = p.psi + (size_t)nb * N * K + k;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                psi[i] = nw[i];
-                if (live) st_cs(o, psi[i]);
-                o += K;
-            }
-        }
-        // the target at the END of segment sb, then through P_sb^dagger
-        if (live) {
-            cplx* o = a.chiE + (size_t)sb * N * K + k;
-#pragma unroll
-            for (int i = 0; i < N; ++i) { *o = y[i]; o += K; }
-        }
-        if (sb > 0) {
-            cplx ny[N];
+        for (int sf = 0; sf < a.NSEG; ++sf) {
+            cp_async_wait<CHAIN_D - 2>();          // this thread's copies of segment sf have landed
+            const cplx* st = ring + (size_t)(sf % CHAIN_D) * NN * CHAIN_BD;
+            cplx nw[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 cplx acc = mk(0.0, 0.0);
 #pragma unroll
-                for (int j = 0; j < N; ++j) cfmac(acc, st[(NN + j * N + i) * CHAIN_BD], y[j]);
-                ny[i] = acc;
+                for (int j = 0; j < N; ++j) cfma(acc, st[(i * N + j) * CHAIN_BD], x[j]);
+                nw[i] = acc;
             }
+            const int nb = min(NT, (sf + 1) * a.S);
+            cplx* o = p.psi + (size_t)nb * N * K + k;
 #pragma unroll
-            for (int i = 0; i < N; ++i) y[i] = ny[i];
+            for (int i = 0; i < N; ++i) {
+                x[i] = nw[i];
+                if (live) st_cs(o, x[i]);
+                o += K;
+            }
+            issue(sf + CHAIN_D - 1);               // refill the slot the previous segment used
         }
-        issue(sf + CHAIN_D - 1);                   // refill the slot segment sf - 1 used (already consumed)
-    }
-    if (live) {
-        cplx acc = mk(0.0, 0.0);
+        if (live) {
+            cplx acc = mk(0.0, 0.0);
 #pragma unroll
-        for (int i = 0; i < N; ++i) cfmac(acc, p.tgt[(size_t)i * K + k], psi[i]);
-        p.tau[k] = acc;
-        p.jb[k] = 0.0;
+            for (int i = 0; i < N; ++i) cfmac(acc, p.tgt[(size_t)i * K + k], x[i]);
+            p.tau[k] = acc;
+            p.jb[k] = 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = p.tgt[(size_t)i * K + kk];
+        for (int it = 0; it < a.NSEG; ++it) {
+            const int sb = a.NSEG - 1 - it;
+            // the target at the END of segment sb, then through P_sb^dagger
+            if (live) {
+                cplx* o = a.chiE + (size_t)sb * N * K + k;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { *o = x[i]; o += K; }
+            }
+            if (sb > 0) {
+                cp_async_wait<CHAIN_D - 2>();
+                const cplx* st = ring + (size_t)(it % CHAIN_D) * NN * CHAIN_BD;
+                cplx ny[N];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    cplx acc = mk(0.0, 0.0);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) cfmac(acc, st[(j * N + i) * CHAIN_BD], x[j]);
+                    ny[i] = acc;
+                }
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] = ny[i];
+                issue(it + CHAIN_D - 1);
+            }
+        }
     }
 }
 

@@ -494,8 +494,8 @@ __device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], c
     }
 }
 
-template <int N, int LT>
-__global__ void __launch_bounds__(SYM_BD, 3) small_seggrad_sym2(DevP p, SegArgs a) {
+template <int N, int LT, int MINB = 3>
+__global__ void __launch_bounds__(SYM_BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
     const int K = p.K, NT = p.NT, L = LT > 0 ? LT : p.L;

@@ -291,7 +291,7 @@ int small_setup(H* h, const grape_b200_problem* d) {
                 full = warps >= resident;
                 // warps drain continuously rather than in lock-step waves: fractional waves, plus half a segment of tail
                 // (measured on C3, profiles/r2_s1_c3_sweep.txt: S = 20..25 beats the S = 38 of a whole-wave model by 2 %)
-                return std::max(1.0, (double)warps / (double)resident) * s_ + 0.5 * s_ + 0.26 * (double)nseg;
+                return std::max(1.0, (double)warps / (double)resident) * s_ + 0.5 * s_ + 0.12 * (double)nseg;   // 0.12: one chain segment (two-warp ring kernel)
             };
             bool full = false;
             double best = cost(S, full);
@@ -301,6 +301,12 @@ int small_setup(H* h, const grape_b200_problem* d) {
                     bool f2;
                     const double c = cost(s_, f2);
                     if (f2 && c < best - 1e-9) { best = c; S = s_; }
+                }
+                // the model is flat (+-1 %) between 45 and 60 segments; the measured optimum of the real-symmetric kernels
+                // on C3 is 46..50 segments (profiles/r2_s11_c3_sweep.txt): take 48 when that still gives >= 2 waves of warps
+                if (h->seg_real) {
+                    const int s48 = (NT + 47) / 48;
+                    if (s48 >= 2 && KGR * (((NT + s48 - 1) / s48 + SPW - 1) / SPW) >= 2 * resident) S = s48;
                 }
             }
         }

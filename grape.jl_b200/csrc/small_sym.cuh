@@ -330,38 +330,38 @@ constexpr int SYM_BD = 128;   // threads per block of the staged kernels
 // dynamic shared memory of the staged kernels, bytes
 inline size_t sym_stage_bytes(int N, int L) { return (size_t)(1 + L) * N * N * SYM_BD * sizeof(double); }
 
-template <int N>
+template <int N, int BD = SYM_BD>
 GB_D void sym_stage(const DevP& p, const SegArgs& a, int g, int L, double* sH) {
     constexpr int NN = N * N;
     const int G = p.G, t = threadIdx.x;
 #pragma unroll
-    for (int c = 0; c < NN; ++c) sH[c * SYM_BD + t] = __ldg(&a.H0r[(size_t)c * G + g]);
+    for (int c = 0; c < NN; ++c) sH[c * BD + t] = __ldg(&a.H0r[(size_t)c * G + g]);
     for (int l = 0; l < L; ++l)
 #pragma unroll
-        for (int c = 0; c < NN; ++c) sH[(NN + l * NN + c) * SYM_BD + t] = __ldg(&a.Hcr[((size_t)l * NN + c) * G + g]);
+        for (int c = 0; c < NN; ++c) sH[(NN + l * NN + c) * BD + t] = __ldg(&a.Hcr[((size_t)l * NN + c) * G + g]);
 }
 
 // Hs = H0 + sum_l a_l Hc_l from the staged tile, and its 1-norm
-template <int N, int LT>
+template <int N, int LT, int BD = SYM_BD>
 GB_D double sym_form_H_staged(const DevP& p, const double* sH, int L, int n, double (&Hs)[N * N]) {
     constexpr int NN = N * N;
     const int NT = p.NT, t = threadIdx.x;
 #pragma unroll
-    for (int c = 0; c < NN; ++c) Hs[c] = sH[c * SYM_BD + t];
+    for (int c = 0; c < NN; ++c) Hs[c] = sH[c * BD + t];
     if (LT > 0) {
 #pragma unroll
         for (int l = 0; l < LT; ++l) {
             double am = p.eps[l * NT + n];
             if (p.shape) am *= p.shape[l * NT + n];
 #pragma unroll
-            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * SYM_BD + t], Hs[c]);
+            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * BD + t], Hs[c]);
         }
     } else {
         for (int l = 0; l < L; ++l) {
             double am = p.eps[l * NT + n];
             if (p.shape) am *= p.shape[l * NT + n];
 #pragma unroll
-            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * SYM_BD + t], Hs[c]);
+            for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * BD + t], Hs[c]);
         }
     }
     double nrm = 0.0;
@@ -494,8 +494,11 @@ __device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], c
     }
 }
 
-template <int N, int LT, int MINB = 3>
-__global__ void __launch_bounds__(SYM_BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
+// BD = 128 (MINB = 3) for GPU-filling ensembles; BD = 64 (MINB = 6, same 168 registers and 12 warps per SM) for shards
+// whose warps do not fill two waves: 364 four-warp blocks on 148 SMs leave SMs with 3 blocks next to SMs with 2 (the
+// kernel takes as long as the former), 728 two-warp blocks balance to 5 / 4.9
+template <int N, int LT, int MINB = 3, int BD = SYM_BD>
+__global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
     const int K = p.K, NT = p.NT, L = LT > 0 ? LT : p.L;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(SYM_BD, MINB) small_seggrad_sym2(DevP p, SegAr
     const int sseg = seg < a.NSEG ? seg : a.NSEG - 1;
     const int n0 = sseg * a.S, n1 = min(NT, n0 + a.S);
     double rho = a.scan ? 1.0 : p.rho[kk];   // scan schedules: computed in the prologue below
-    sym_stage<N>(p, a, p.gen[kk], L, sH);
+    sym_stage<N, BD>(p, a, p.gen[kk], L, sH);
 
     cplx chi[N], psi[N];
     if (a.scan == 2) {
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(SYM_BD, MINB) small_seggrad_sym2(DevP p, SegAr
         const int nn = n >= n0 ? n : n0;
         const double dt = p.tlist[nn + 1] - p.tlist[nn];
         double Hs[NN];
-        const double theta = dt * sym_form_H_staged<N, LT>(p, sH, L, nn, Hs);
+        const double theta = dt * sym_form_H_staged<N, LT, BD>(p, sH, L, nn, Hs);
         int m = 2;
 #pragma unroll
         for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(SYM_BD, MINB) small_seggrad_sym2(DevP p, SegAr
             if (p.dshape) sl *= p.dshape[l * NT + nn];
             double acc = 0.0;
 #pragma unroll
-            for (int c = 0; c < NN; ++c) acc = fma(sH[(NN + l * NN + c) * SYM_BD + threadIdx.x], IM[c], acc);
+            for (int c = 0; c < NN; ++c) acc = fma(sH[(NN + l * NN + c) * BD + threadIdx.x], IM[c], acc);
             return act ? sl * acc : 0.0;
         };
         if (LT > 0) {

@@ -513,13 +513,8 @@ void seg_grad_t(H* h) {
             run_if = a.notfast;
         } else {
             // staged kernels: every step is served (sub-stepping inside), no second launch
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-            const bool narrow = warps < 2ll * 12 * sms &&   // under two waves of warps: two-warp blocks balance the SMs
-                                !(getenv("GRAPE_B200_SYM_BD") && atoi(getenv("GRAPE_B200_SYM_BD")) == 128);
-            if (narrow && h->p.L == 2) small_seggrad_sym2<NS, 2, 6, 64><<<(unsigned)((warps + 1) / 2), 64, sm / 2, h->stream>>>(h->p, a);
-            else if (narrow && h->p.L == 1) small_seggrad_sym2<NS, 1, 6, 64><<<(unsigned)((warps + 1) / 2), 64, sm / 2, h->stream>>>(h->p, a);
-            else if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            // (two-warp blocks for under-filled launches were measured: no difference, profiles/r2_s13_c3_sweep.txt)
+            if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else if (h->p.L == 2 && h->sym_occ == 4) small_seggrad_sym2<NS, 2, 4><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: 128 registers
             else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);

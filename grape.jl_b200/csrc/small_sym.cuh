@@ -494,9 +494,8 @@ __device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], c
     }
 }
 
-// BD = 128 (MINB = 3) for GPU-filling ensembles; BD = 64 (MINB = 6, same 168 registers and 12 warps per SM) for shards
-// whose warps do not fill two waves: 364 four-warp blocks on 148 SMs leave SMs with 3 blocks next to SMs with 2 (the
-// kernel takes as long as the former), 728 two-warp blocks balance to 5 / 4.9
+// BD / MINB: 128 threads, 3 blocks per SM (168 registers, 12 warps).  Two-warp blocks (BD = 64, MINB = 6) for
+// under-filled launches and a 128-register build (MINB = 4) were measured and are not used (no gain / 8 % slower).
 template <int N, int LT, int MINB = 3, int BD = SYM_BD>
 __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;

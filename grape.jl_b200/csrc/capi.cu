@@ -239,7 +239,7 @@ int small_setup(H* h, const grape_b200_problem* d) {
             h->seg_real = real;
             h->sym_occ = getenv("GRAPE_B200_SYM_OCC") ? atoi(getenv("GRAPE_B200_SYM_OCC")) : 3;
             h->sym_v = getenv("GRAPE_B200_SYM_V") ? atoi(getenv("GRAPE_B200_SYM_V")) : 2;
-            if (getenv("GRAPE_B200_SYM_OCC") && h->sym_occ != 4) h->sym_v = 1;   // 2 / 3: occupancy variants of the round-1 kernels; 4: A/B variant of the staged gradient kernel
+            if (getenv("GRAPE_B200_SYM_OCC") && h->sym_occ < 4) h->sym_v = 1;   // 2 / 3: occupancy variants of the round-1 kernels; 4: A/B variant of the staged gradient kernel
             if (real && h->sym_v != 1) {
                 // per-thread operator tile of the staged kernels: (1 + L) N^2 doubles x 128 threads
                 const size_t sm = sym_stage_bytes(N, L);
@@ -516,6 +516,7 @@ void seg_grad_t(H* h) {
             // (two-warp blocks for under-filled launches were measured: no difference, profiles/r2_s13_c3_sweep.txt)
             if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else if (h->p.L == 2 && h->sym_occ == 4) small_seggrad_sym2<NS, 2, 4><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: 128 registers
+            else if (h->p.L == 2 && h->sym_occ == 5) small_seggrad_sym2<NS, 2, 3, SYM_BD, false><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: no prefetch of the next step's pulse values
             else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             h->launches++;

@@ -342,6 +342,33 @@ GB_D void sym_stage(const DevP& p, const SegArgs& a, int g, int L, double* sH) {
 }
 
 // Hs = H0 + sum_l a_l Hc_l from the staged tile, and its 1-norm
+// amplitude of control l at step n (eps * shape; in amplitude mode eps holds the amplitude itself and shape is off)
+GB_D double sym_amp(const DevP& p, int l, int n) {
+    double am = p.eps[l * p.NT + n];
+    if (p.shape) am *= p.shape[l * p.NT + n];
+    return am;
+}
+// Hs = H0 + sum_l am[l] Hc_l from the staged tile with the amplitudes already in registers, and its 1-norm
+template <int N, int LT, int BD = SYM_BD>
+GB_D double sym_form_H_amps(const double* sH, const double (&am)[LT > 0 ? LT : 1], double (&Hs)[N * N]) {
+    constexpr int NN = N * N;
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < NN; ++c) Hs[c] = sH[c * BD + t];
+#pragma unroll
+    for (int l = 0; l < LT; ++l)
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Hs[c] = fma(am[l], sH[(NN + l * NN + c) * BD + t], Hs[c]);
+    double nrm = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
+        nrm = fmax(nrm, s);
+    }
+    return nrm;
+}
 template <int N, int LT, int BD = SYM_BD>
 GB_D double sym_form_H_staged(const DevP& p, const double* sH, int L, int n, double (&Hs)[N * N]) {
     constexpr int NN = N * N;
@@ -496,7 +523,7 @@ __device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], c
 
 // BD / MINB: 128 threads, 3 blocks per SM (168 registers, 12 warps).  Two-warp blocks (BD = 64, MINB = 6) for
 // under-filled launches and a 128-register build (MINB = 4) were measured and are not used (no gain / 8 % slower).
-template <int N, int LT, int MINB = 3, int BD = SYM_BD>
+template <int N, int LT, int MINB = 3, int BD = SYM_BD, bool PF = true>
 __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
@@ -624,13 +651,36 @@ __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a
     }
     double* const part = p.partial + (size_t)kg * L * NT;
     const bool writer = tk == 0 && seg < a.NSEG;
+    // the pulse values and the step width of the NEXT step are fetched while the current step computes (their L1
+    // round trip sat at the head of every step's dependency chain)
+    double am_next[LT > 0 ? LT : 1], dt_next;
+    {
+        const int nf = n1 - 1 >= n0 ? n1 - 1 : n0;
+        dt_next = p.tlist[nf + 1] - p.tlist[nf];
+#pragma unroll
+        for (int l = 0; l < LT; ++l) am_next[l] = sym_amp(p, l, nf);
+    }
     for (int st = 0; st < a.S; ++st) {   // uniform trip count across the warp
         const int n = n1 - 1 - st;
         const bool act = live && n >= n0;
         const int nn = n >= n0 ? n : n0;
-        const double dt = p.tlist[nn + 1] - p.tlist[nn];
+        const double dt = dt_next;
         double Hs[NN];
-        const double theta = dt * sym_form_H_staged<N, LT, BD>(p, sH, L, nn, Hs);
+        double theta;
+        if (LT > 0 && PF) {
+            double am[LT > 0 ? LT : 1];
+#pragma unroll
+            for (int l = 0; l < LT; ++l) am[l] = am_next[l];
+            const int nx = n - 1 >= n0 ? n - 1 : n0;
+            dt_next = p.tlist[nx + 1] - p.tlist[nx];
+#pragma unroll
+            for (int l = 0; l < LT; ++l) am_next[l] = sym_amp(p, l, nx);
+            theta = dt * sym_form_H_amps<N, LT, BD>(sH, am, Hs);
+        } else {
+            const int nx = n - 1 >= n0 ? n - 1 : n0;
+            dt_next = p.tlist[nx + 1] - p.tlist[nx];
+            theta = dt * sym_form_H_staged<N, LT, BD>(p, sH, L, nn, Hs);
+        }
         int m = 2;
 #pragma unroll
         for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;

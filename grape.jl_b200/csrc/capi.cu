@@ -516,7 +516,7 @@ void seg_grad_t(H* h) {
             // (two-warp blocks for under-filled launches were measured: no difference, profiles/r2_s13_c3_sweep.txt)
             if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else if (h->p.L == 2 && h->sym_occ == 4) small_seggrad_sym2<NS, 2, 4><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: 128 registers
-            else if (h->p.L == 2 && h->sym_occ == 5) small_seggrad_sym2<NS, 2, 3, SYM_BD, false><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: no prefetch of the next step's pulse values
+            else if (h->p.L == 2 && h->sym_occ == 5) small_seggrad_sym2<NS, 2, 3, SYM_BD, true><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: prefetch of the next step's pulse values
             else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             h->launches++;

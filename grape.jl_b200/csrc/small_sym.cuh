@@ -523,7 +523,7 @@ __device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], c
 
 // BD / MINB: 128 threads, 3 blocks per SM (168 registers, 12 warps).  Two-warp blocks (BD = 64, MINB = 6) for
 // under-filled launches and a 128-register build (MINB = 4) were measured and are not used (no gain / 8 % slower).
-template <int N, int LT, int MINB = 3, int BD = SYM_BD, bool PF = true>
+template <int N, int LT, int MINB = 3, int BD = SYM_BD, bool PF = false>
 __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
@@ -651,8 +651,8 @@ __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a
     }
     double* const part = p.partial + (size_t)kg * L * NT;
     const bool writer = tk == 0 && seg < a.NSEG;
-    // the pulse values and the step width of the NEXT step are fetched while the current step computes (their L1
-    // round trip sat at the head of every step's dependency chain)
+    // PF: the pulse values and the step width of the NEXT step are fetched while the current step computes.  Measured:
+    // no gain (profiles/r2_s14_c3_ab.txt: 0.3789 ms with and without), so the default is the plain form.
     double am_next[LT > 0 ? LT : 1], dt_next;
     {
         const int nf = n1 - 1 >= n0 ? n1 - 1 : n0;

@@ -303,9 +303,10 @@ int small_setup(H* h, const grape_b200_problem* d) {
                     if (f2 && c < best - 1e-9) { best = c; S = s_; }
                 }
                 // the model is flat (+-1 %) between 45 and 60 segments; the measured optimum of the real-symmetric kernels
-                // on C3 is 46..50 segments (profiles/r2_s11_c3_sweep.txt): take 48 when that still gives >= 2 waves of warps
+                // on C3 is 50 segments (S = 20: profiles/r2_s11_c3_sweep.txt, r2_s15_c3_S.txt: 0.369 ms against 0.373 at 40 and 0.379 at 44 / 48
+                // segments, three interleaved repetitions): take 50 when that still gives >= 2 waves of warps
                 if (h->seg_real) {
-                    const int s48 = (NT + 47) / 48;
+                    const int s48 = (NT + 49) / 50;
                     if (s48 >= 2 && KGR * (((NT + s48 - 1) / s48 + SPW - 1) / SPW) >= 2 * resident) S = s48;
                 }
             }

@@ -66,6 +66,8 @@ SYMBOLS = {
     "grape_b200_gradient_form": (C.c_int, [_P]),
     "grape_b200_small_schedule": (C.c_int, [_P]),
     "grape_b200_dense_concurrent": (C.c_int, [_P]),
+    "grape_b200_dense_orders": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "grape_b200_econ_table": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "grape_b200_xchg_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "grape_b200_xchg_attach": (C.c_int, [_P, _P]),
     "grape_b200_xchg_detach": (C.c_int, [_P]),

@@ -1416,6 +1416,25 @@ int grape_b200_dense_concurrent(grape_b200_handle* h) {
     return ok ? 1 : 0;
 }
 
+int grape_b200_dense_orders(grape_b200_handle* h, int* orders) {
+    if (!h || !orders) return -GRAPE_B200_EINVAL;
+    if (h->path != GRAPE_B200_PATH_DENSE || !h->dense.kd.on) { if (h) h->err = "no Krylov-form schedule on this handle"; return -GRAPE_B200_EINVAL; }
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess ||
+        cudaMemcpy(orders, h->dense.kd.m_n, sizeof(int) * (size_t)h->p.NT, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        h->err = "CUDA error while reading the step orders";
+        return -GRAPE_B200_ECUDA;
+    }
+    return h->dense.d.econ ? 1 : 0;
+}
+
+int grape_b200_econ_table(int m, double* theta, double* g) {
+    if (m < 2 || m > ECON_MAXM || !theta || !g) return GRAPE_B200_EINVAL;
+    const EconTab& t = econ_table();
+    *theta = t.theta[m];
+    for (int j = 0; j <= m; ++j) g[j] = t.g[m][j];
+    return 0;
+}
+
 int grape_b200_small_schedule(grape_b200_handle* h) {
     if (!h) return -GRAPE_B200_EINVAL;
     if (h->path != GRAPE_B200_PATH_SMALL || !h->seg_on) return 0;

@@ -71,6 +71,7 @@ struct DenseDev {
     const double* PTa;
     int tma;       // strip prefetch through the TMA copy engine (cp.async.bulk + mbarrier) instead of per-thread cp.async
     int herm;      // every operator equals its adjoint (exact): backward chains read the forward generators
+    int econ;      // Hermitian generators: Krylov-form chains sum the economised polynomial (c_econ) instead of the Taylor series
     int nP;        // (L+1)(L+2)/2 pair products
     const double* PPf;  // [nP][2][Np][Np]  H_i H_j + H_j H_i (i < j), H_i^2 (i == j), pair order (0,0),(0,1)..(0,L),(1,1)..(L,L)
     const double* PPa;  // the same products of the adjoints
@@ -303,14 +304,107 @@ GB_D cplx dense_reduce(double* __restrict__ red, DAcc (&acc)[NG], int ng) {
     return res;
 }
 
-GB_D void dense_plan(const DevP& p, const DenseDev& d, int n, double dt, int& m, int& s) {
+// ---------------------------------------------------------------------------
+// Economised exponential for Hermitian generators (the Chebyshev propagator of the reference's tutorials,
+// docs/src/tutorial.md:308, 432, re-expressed in the monomial basis the Krylov-form gradient needs).
+// exp(-i x) on [-Theta, Theta] is the Chebyshev series J_0(Theta) + 2 sum_k (-i)^k J_k(Theta) T_k(x / Theta); cut at
+// degree m its uniform error is 2 sum_{k>m} |J_k(Theta)| ~ 2 (Theta/2)^(m+1) / (m+1)!, a factor 2^m below the Taylor
+// remainder, so a step of ||H dt|| = 0.5 needs degree 12 instead of 15..16.  Written in powers of x the cut series is
+//     p_m(x) = sum_{j<=m} g[m][j] (-i x)^j / j!,   g[m][j] = j!/Theta^j sum_{k=j,j+2,..<=m} w_k J_k(Theta) |t_kj|  (real, ~ 1),
+// (t_kj: coefficient of y^j in T_k, w_0 = 1, w_k = 2): the chains keep generating the TAYLOR terms (the Krylov vectors
+// bh_j, ch_j of dense_kry.cuh) and only weigh them with g when summing the new state; the gradient of the polynomial
+// propagator is exact with beta(a,b) g[m][a+b+1].  theta[m] = the largest Theta (<= 1) whose error bound is <= 1e-17.
+// Only with every operator Hermitian (spectrum of H_n dt inside [-||H_n dt||, ||H_n dt||]) and only on the Krylov-form
+// schedule; the block recursion (:taylor, sub-stepped calls, non-Hermitian generators) keeps the Taylor series.
+// ---------------------------------------------------------------------------
+constexpr int ECON_MAXM = KRY_MTMAX;
+constexpr double ECON_TOL = 1e-17;
+struct EconTab {
+    double theta[ECON_MAXM + 1];
+    double g[ECON_MAXM + 1][ECON_MAXM + 1];
+    double ones[ECON_MAXM + 1];
+};
+__constant__ EconTab c_econ;
+
+inline long double econ_besselj(int k, long double x) {   // power series, x <= 1
+    long double term = 1.0L;
+    for (int i = 1; i <= k; ++i) term *= (x / 2) / i;
+    long double sum = term;
+    for (int i = 1; i < 60; ++i) {
+        term *= -(x / 2) * (x / 2) / ((long double)i * (k + i));
+        sum += term;
+        if (fabsl(term) < 1e-40L) break;
+    }
+    return sum;
+}
+inline long double econ_err(int m, long double th) {
+    long double e = 0.0L;
+    for (int k = m + 1; k < m + 40; ++k) e += fabsl(econ_besselj(k, th));
+    return 2 * e;
+}
+inline const EconTab& econ_table() {
+    static EconTab tab;
+    static bool built = false;
+    if (built) return tab;
+    memset(&tab, 0, sizeof tab);
+    // |t_kj| of the Chebyshev polynomials: T_{k+1} = 2 y T_k - T_{k-1}
+    static long double T[ECON_MAXM + 1][ECON_MAXM + 1];
+    memset(T, 0, sizeof T);
+    T[0][0] = 1.0L;
+    T[1][1] = 1.0L;
+    for (int k = 2; k <= ECON_MAXM; ++k)
+        for (int j = 0; j <= k; ++j) T[k][j] = (j ? 2 * T[k - 1][j - 1] : 0.0L) + T[k - 2][j];   // magnitudes add (signs alternate)
+    for (int m = 0; m <= ECON_MAXM; ++m) {
+        tab.ones[m] = 1.0;
+        for (int j = 0; j <= ECON_MAXM; ++j) tab.g[m][j] = 1.0;
+        if (m < 2) continue;
+        long double lo = 0.0L, hi = 1.0L;
+        if (econ_err(m, hi) <= (long double)ECON_TOL) lo = hi;
+        else
+            for (int it = 0; it < 70; ++it) {
+                const long double mid = (lo + hi) / 2;
+                if (econ_err(m, mid) <= (long double)ECON_TOL) lo = mid; else hi = mid;
+            }
+        tab.theta[m] = (double)lo;
+        if ((long double)tab.theta[m] > lo) tab.theta[m] = nextafter(tab.theta[m], 0.0);
+        const long double th = lo;
+        if (th <= 0.0L) continue;
+        long double fj = 1.0L, thj = 1.0L;   // j!, Theta^j
+        for (int j = 0; j <= m; ++j) {
+            if (j) { fj *= j; thj *= th; }
+            long double sacc = 0.0L;
+            for (int k = j; k <= m; k += 2) sacc += (k ? 2.0L : 1.0L) * econ_besselj(k, th) * T[k][j];
+            tab.g[m][j] = (double)(sacc * fj / thj);
+        }
+    }
+    built = true;
+    return tab;
+}
+
+// Taylor order / sub-steps of step n (block recursion), or -- econ -- the degree and weights of the economised polynomial
+GB_D double dense_theta(const DevP& p, const DenseDev& d, int n, double dt) {
     double nrm = d.hnorm[0];
     for (int l = 0; l < p.L; ++l) {
         double a = p.eps[l * p.NT + n];
         if (p.shape) a *= p.shape[l * p.NT + n];
         nrm += fabs(a) * d.hnorm[1 + l];
     }
-    vec_plan(nrm * dt, m, s);
+    return nrm * dt;
+}
+GB_D void dense_plan(const DevP& p, const DenseDev& d, int n, double dt, int& m, int& s) {
+    vec_plan(dense_theta(p, d, n, dt), m, s);
+}
+GB_D void dense_plan(const DevP& p, const DenseDev& d, int n, double dt, int& m, int& s, const double*& gw, bool econ) {
+    const double th = dense_theta(p, d, n, dt);
+    gw = c_econ.ones;
+    if (econ && th <= c_econ.theta[ECON_MAXM]) {
+        m = 2;
+        while (c_econ.theta[m] < th) ++m;
+        s = 0;
+        gw = c_econ.g[m];
+        return;
+    }
+    vec_plan(th, m, s);
 }
 
 // rows r0..r0+7 of  H0 + sum_l a_l Hc_l  (or of the adjoints) into shared memory; the 2 x 8 loads of a trip and
@@ -649,7 +743,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
         else if (DUAL && pre) cp_async_wait<0>();   // strips of this step: issued behind the previous step's last stage
         else dense_form_H(p, Hall, Np, MS, r0, n, Hs_re, Hs_im);
         int m, s;
-        dense_plan(p, d, n, dt, m, s);
+        const double* gw;   // weights of the Taylor terms in the new state (1, or the economised polynomial's)
+        dense_plan(p, d, n, dt, m, s, gw, d.econ && kd.on);
         if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && bid == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
         const bool kry = kd.on && s == 0 && m <= kd.MT;
@@ -722,8 +817,9 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                                         dst[off] = tr;
                                         dst[splane + off] = ti;
                                     }
-                                    ar += tr;
-                                    ai += ti;
+                                    const double gq = gw[j + q + 1];
+                                    ar = fma(gq, tr, ar);
+                                    ai = fma(gq, ti, ai);
                                 }
                                 acc_re[nrow * Ccap + cglob - cbeg] = ar;
                                 acc_im[nrow * Ccap + cglob - cbeg] = ai;
@@ -753,8 +849,9 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                                         dst[off] = tr;
                                         dst[splane + off] = ti;
                                     }
-                                    acc_re[nrow * Ccap + cglob - cbeg] += tr;
-                                    acc_im[nrow * Ccap + cglob - cbeg] += ti;
+                                    const double gq = gw[j + q + 1];
+                                    acc_re[nrow * Ccap + cglob - cbeg] = fma(gq, tr, acc_re[nrow * Ccap + cglob - cbeg]);
+                                    acc_im[nrow * Ccap + cglob - cbeg] = fma(gq, ti, acc_im[nrow * Ccap + cglob - cbeg]);
                                 }
                             }
                         }
@@ -794,8 +891,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1) dense_chain(DevP p, DenseDev
                             dst[(size_t)(r0 + nrow) * Kp + cglob] = tr;
                             dst[splane + (size_t)(r0 + nrow) * Kp + cglob] = ti;
                         }
-                        acc_re[nrow * Ccap + cglob - cbeg] += tr;
-                        acc_im[nrow * Ccap + cglob - cbeg] += ti;
+                        acc_re[nrow * Ccap + cglob - cbeg] = fma(gw[j], tr, acc_re[nrow * Ccap + cglob - cbeg]);
+                        acc_im[nrow * Ccap + cglob - cbeg] = fma(gw[j], ti, acc_im[nrow * Ccap + cglob - cbeg]);
                     }
                 }
                 if (j < m) grid.sync();
@@ -1262,6 +1359,12 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
     if ((rc = upd(hf, &d.Hf))) return rc;
     if ((rc = upd(ha, &d.Ha))) return rc;
     d.herm = (hf == ha) ? 1 : 0;
+    {
+        // economised polynomial instead of the Taylor series on the Krylov-form schedule (GRAPE_B200_ECON=0: Taylor)
+        const char* e = getenv("GRAPE_B200_ECON");
+        d.econ = d.herm && !(e && atoi(e) == 0);
+        if (cudaMemcpyToSymbol(c_econ, &econ_table(), sizeof(EconTab)) != cudaSuccess) { err = "cudaMemcpyToSymbol failed (economised-polynomial table)"; return GRAPE_B200_ECUDA; }
+    }
     if (p.gb_kind) {
         std::vector<double> dm(2 * hplane, 0.0);
         for (int i = 0; i < N; ++i)

@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
         const double* Hn = d2.Hn[n & 1];
         if (!BWD && gb) gb_point(n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]));
         int m, s;
-        dense_plan(p, d, n, dt, m, s);
+        const double* gw;   // weights of the Taylor terms in the new state (dense.cuh: economised polynomial)
+        dense_plan(p, d, n, dt, m, s, gw, d.econ && kd.on);
         if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
         const bool kry = kd.on && s == 0 && m <= kd.MT;
@@ -377,8 +378,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain(DevP p, DenseDev d
                         tr[e] = BWD ? -x * acc[0].im[e] : x * acc[0].im[e];
                         ti[e] = BWD ? x * acc[0].re[e] : -x * acc[0].re[e];
                     }
-                    vr[0] = b_r.x + tr[0]; vr[1] = b_r.y + tr[1];
-                    vi[0] = b_i.x + ti[0]; vi[1] = b_i.y + ti[1];
+                    vr[0] = fma(gw[j], tr[0], b_r.x); vr[1] = fma(gw[j], tr[1], b_r.y);
+                    vi[0] = fma(gw[j], ti[0], b_i.x); vi[1] = fma(gw[j], ti[1], b_i.y);
                     if (j < m) {
                         *reinterpret_cast<double2*>(&dst[off]) = make_double2(tr[0], tr[1]);
                         *reinterpret_cast<double2*>(&dst[splane + off]) = make_double2(ti[0], ti[1]);
@@ -895,7 +896,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain_multi(DevP p, Dens
         const double* Hq = pre + (size_t)n * (2 * NS) * hplane;   // planes {Re H, Im H, Re H^2, Im H^2, ..}
         if (!BWD && gb) gb_point(n == 0 ? 0.5 * (p.tlist[1] - p.tlist[0]) : 0.5 * (p.tlist[n + 1] - p.tlist[n - 1]));
         int m, s;
-        dense_plan(p, d, n, dt, m, s);
+        const double* gw;   // weights of the Taylor terms in the new state (dense.cuh: economised polynomial)
+        dense_plan(p, d, n, dt, m, s, gw, d.econ && kd.on);
         if (!BWD && p.grad_method != 0 && p.taylor_check && m > p.taylor_max_order && blockIdx.x == 0 && threadIdx.x == 0)
             p.flags->taylor_fail = 1;
         const bool kry = kd.on && s == 0 && m <= kd.MT;
@@ -938,8 +940,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dense2_chain_multi(DevP p, Dens
                                 if (q == 0) { tr[e] = BWD ? -x * acc[q].im[e] : x * acc[q].im[e]; ti[e] = BWD ? x * acc[q].re[e] : -x * acc[q].re[e]; }
                                 else if (q == 1) { tr[e] = -x * acc[q].re[e]; ti[e] = -x * acc[q].im[e]; }
                                 else { tr[e] = BWD ? x * acc[q].im[e] : -x * acc[q].im[e]; ti[e] = BWD ? -x * acc[q].re[e] : x * acc[q].re[e]; }
-                                vr[e] += tr[e];
-                                vi[e] += ti[e];
+                                vr[e] = fma(gw[j + q], tr[e], vr[e]);
+                                vi[e] = fma(gw[j + q], ti[e], vi[e]);
                             }
                             if (j + q < m) {
                                 double* dst = kry ? slots + (size_t)(j + q) * 2 * splane : (((j + q) & 1) ? d.T1 : d.T0);

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) kry_plan(DevP p, DenseDev d, KryDev kd) {
     __syncthreads();
     for (int n = threadIdx.x; n < p.NT; n += blockDim.x) {
         int m, s;
-        dense_plan(p, d, n, p.tlist[n + 1] - p.tlist[n], m, s);
+        const double* gw;
+        dense_plan(p, d, n, p.tlist[n + 1] - p.tlist[n], m, s, gw, d.econ != 0);
         kd.m_n[n] = m;
         if (s != 0 || m > kd.MT) atomicOr(&s_bad, 1);
     }
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) kry_combine(DevP p, DenseDev d, KryDev kd
             const size_t r = e % slot;
             const int k = (int)(r % d.Kp);
             const int m = kd.m_n[n];
+            const double* gw = d.econ ? c_econ.g[m] : c_econ.ones;   // a call served here has s == 0 in every step: all economised
             const double rho = k < p.K ? p.rho[k] : 0.0;
             double* ft = kd.FT + (size_t)n * kd.MT * slot + r;
             double v[KRY_MTMAX];
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(256) kry_combine(DevP p, DenseDev d, KryDev kd
                     double s = 0.0;
 #pragma unroll
                     for (int a = 0; a < KRY_MTMAX - b; ++a)
-                        if (a < m - b) s = fma(c_kbeta.v[a][b], v[a], s);
+                        if (a < m - b) s = fma(c_kbeta.v[a][b] * gw[a + b + 1], v[a], s);
                     ft[(size_t)b * slot] = rho * s;
                 }
             }
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256) kry_combine(DevP p, DenseDev d, KryDev kd
         const size_t r = e % splane;
         const int k = (int)(r % d.Kp);
         const int m = kd.m_n[n];
+        const double* gw = d.econ ? c_econ.g[m] : c_econ.ones;
         const double fr = k < p.K ? kd.kfac[k] : 0.0, fi = k < p.K ? kd.kfac[d.Kp + k] : 0.0;
         double* ft = kd.FT + (size_t)n * kd.MT * slot + r;
         double vr[KRY_MTMAX], vi[KRY_MTMAX];
@@ -113,7 +116,11 @@ __global__ void __launch_bounds__(256) kry_combine(DevP p, DenseDev d, KryDev kd
                 double sr = 0.0, si = 0.0;
 #pragma unroll
                 for (int a = 0; a < KRY_MTMAX - b; ++a)
-                    if (a < m - b) { sr = fma(c_kbeta.v[a][b], vr[a], sr); si = fma(c_kbeta.v[a][b], vi[a], si); }
+                    if (a < m - b) {
+                        const double bg = c_kbeta.v[a][b] * gw[a + b + 1];
+                        sr = fma(bg, vr[a], sr);
+                        si = fma(bg, vi[a], si);
+                    }
                 ft[(size_t)b * slot] = fr * sr - fi * si;
                 ft[(size_t)b * slot + splane] = fr * si + fi * sr;
             }

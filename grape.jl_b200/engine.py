@@ -217,6 +217,15 @@ class GrapeEngine:
             self._check(-rc)
         return rc
 
+    def dense_orders(self):
+        """(econ, orders): polynomial degree of every time step in the last call of the dense path's Krylov-form
+        schedule; econ = True if the chains summed the economised (Chebyshev-cut) polynomial instead of the Taylor series."""
+        out = np.zeros(self.problem.NT, dtype=np.int32)
+        rc = int(self.lib.grape_b200_dense_orders(self._h, out.ctypes.data_as(C.POINTER(C.c_int))))
+        if rc < 0:
+            self._check(-rc)
+        return bool(rc), out
+
     def small_schedule(self):
         """0: not the segmented small path, 1: general, 2: Hermitian, 3: real-symmetric schedule served the last gradient."""
         rc = int(self.lib.grape_b200_small_schedule(self._h))

@@ -237,6 +237,14 @@ int grape_b200_gradient_form(grape_b200_handle* h);
  * 880-896), 0 if the sweeps ran one after the other (state running cost, host chi, sub-stepped steps, :taylor).
  * Instrumentation; synchronises the stream. Negative: error code. */
 int grape_b200_dense_concurrent(grape_b200_handle* h);
+/* Polynomial degree of every time step of the dense path's Krylov-form schedule in the last call (orders[NT]); returns
+ * 1 if the chains summed the economised (Chebyshev-cut) polynomial of exp(-i H dt) -- Hermitian generators, csrc/dense.cuh,
+ * the reference's Cheby propagator (docs/src/tutorial.md:308, 432) in the monomial basis --, 0 for the Taylor series
+ * (the reference's series of src/optimize.jl:604-653). Instrumentation; synchronises. Negative: error code. */
+int grape_b200_dense_orders(grape_b200_handle* h, int* orders);
+/* Host-only (no GPU): the economised polynomial of degree m (2..20): *theta = the largest ||H dt|| it serves with a
+ * uniform error <= 1e-17, g[0..m] = the weights of the Taylor terms (-i H dt)^j / j!.  Test instrumentation. */
+int grape_b200_econ_table(int m, double* theta, double* g);
 /* Which schedule of the small path (N <= 4) served the last gradient call (instrumentation; synchronises):
  *   0 = not the time-segmented small path (plain chains, sub-warp or dense path),
  *   1 = time-segmented, general generators (forward states read back from fw_storage),

@@ -138,3 +138,44 @@ def test_julia_shim_matches_header():
     assert [f[0] for f in _lib.ProblemDesc._fields_] == [f[0] for f in j_fields]
     for sym in re.findall(r"ccall\(\(:(\w+),", jl):
         assert sym in _lib.SYMBOLS, sym
+
+
+def test_economised_polynomial_table(lib_built):
+    """csrc/dense.cuh econ_table (host-only entry point): for every degree m the weights g[j] of the Taylor terms give
+    a polynomial within 1e-17 (+ coefficient rounding) of exp(-i x) on [-theta_m, theta_m] (mpmath, 40 digits), theta_m grows with m and is well
+    above the radius the Taylor series of the same degree serves -- the reference's Cheby propagator
+    (docs/src/tutorial.md:308, 432) in the monomial basis."""
+    import ctypes as C
+    import math
+
+    import mpmath as mp
+
+    from grape.jl_b200 import _lib
+    lib = _lib.load()
+    mp.mp.dps = 40
+    prev = 0.0
+    for m in range(2, 21):
+        th = C.c_double()
+        g = (C.c_double * (m + 1))()
+        assert lib.grape_b200_econ_table(m, C.byref(th), g) == 0
+        theta = th.value
+        assert theta >= prev and theta <= 1.0
+        prev = theta
+        if theta == 0.0:
+            continue
+        taylor_radius = (2e-17 * math.factorial(m)) ** (1.0 / m)
+        assert theta >= min(1.0, 1.5 * taylor_radius), (m, theta, taylor_radius)
+        worst = mp.mpf(0)
+        for i in range(0, 41):
+            x = mp.mpf(theta) * (2 * mp.mpf(i) / 40 - 1)
+            pm = sum(mp.mpf(g[j]) * (-1j * x) ** j / mp.factorial(j) for j in range(m + 1))
+            worst = max(worst, abs(pm - mp.exp(-1j * x)))
+        # truncation bound 1e-17 + the rounding of the weights to double (g_0 = 1 - O(1e-17) rounds to 1; g_1 x: up to
+        # 1.1e-16 theta): all an order of magnitude below the rounding of one matrix-vector product
+        assert worst <= 2.02e-17 + 1.2e-16 * theta, (m, theta, float(worst))
+        assert abs(g[0] - 1.0) <= 1e-15 and all(0.9 < g[j] <= 1.0 + 1e-15 for j in range(m + 1))
+    assert lib.grape_b200_econ_table(1, C.byref(th), g) != 0
+    th12 = C.c_double()
+    g12 = (C.c_double * 13)()
+    lib.grape_b200_econ_table(12, C.byref(th12), g12)
+    assert th12.value >= 0.525   # C4 / C5: ||H_n dt|| <= 0.525 -> degree 12 = four 3-term stages (Taylor: 15..16)

@@ -348,3 +348,57 @@ def test_tma_strip_prefetch_matches_cp_async(lib_built, conc):
         out.append(G.copy())
         e.close()
     assert np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("dense2", [0, 1])
+def test_economised_polynomial_orders_and_parity(lib_built, dense2):
+    """Hermitian generators: the Krylov-form chains sum the Chebyshev-cut polynomial of exp(-i H dt) (csrc/dense.cuh
+    econ_table; the reference's Cheby propagator, docs/src/tutorial.md:308, 432, in the monomial basis) -- degree <= 12
+    where the Taylor series needs 13..16 terms at ||H dt|| <= 0.525 --, the gradient is the exact derivative of that
+    polynomial (beta(a,b) g[a+b+1]); both series match the oracle at 1e-10 and each other far below that."""
+    p, eps = configs.c5_dense1024(N=64, K=16, NT=12)
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    scale = max(np.max(np.abs(ref["G"])), 1e-6)
+    got = {}
+    for econ in (1, 0):
+        with _Env(GRAPE_B200_ECON=econ, GRAPE_B200_DENSE2=dense2):
+            e = engine(p)
+        G = np.zeros_like(eps)
+        J = e.evaluate_gradient(G, eps)
+        assert e.gradient_form() > 0
+        flag, orders = e.dense_orders()
+        assert flag == bool(econ)
+        assert abs(J - ref["J"]) <= 1e-10 * max(1.0, abs(ref["J"]))
+        assert np.max(np.abs(G - ref["G"])) <= 1e-10 * scale
+        assert np.max(np.abs(e.tau_vals - ref["tau"])) <= 1e-10
+        assert abs(e.evaluate_functional(eps) - J) <= 1e-13 * max(1.0, abs(J))
+        got[econ] = (J, G, orders)
+        e.close()
+    assert got[1][2].max() <= 12 and got[0][2].min() >= 13, (got[1][2], got[0][2])
+    assert abs(got[1][0] - got[0][0]) <= 1e-13 * max(1.0, abs(got[0][0]))
+    assert np.max(np.abs(got[1][1] - got[0][1])) <= 1e-12 * scale
+
+
+def test_economised_polynomial_only_for_hermitian_generators(lib_built):
+    p, eps = configs.random_problem(K=8, N=40, L=2, NT=5, G=1, seed=77, hermitian=False)
+    p.tlist = p.tlist * (0.5 / np.sqrt(p.N))
+    e, ref = check(p, eps)
+    assert e.gradient_form() > 0
+    flag, orders = e.dense_orders()
+    assert flag is False
+    e.close()
+
+
+def test_economised_polynomial_long_chain_unitarity(lib_built):
+    """1000 steps of the economised polynomial: the final states keep their norm to 1e-12 (a per-step error of 1e-17
+    accumulates linearly at worst) and J matches the Taylor-series run to 1e-12."""
+    p, eps = configs.c4_dense450(N=96, K=8, NT=1000)
+    vals = {}
+    for econ in (1, 0):
+        with _Env(GRAPE_B200_ECON=econ):
+            e = engine(p)
+        vals[econ] = e.evaluate_functional(eps)
+        psi = e.final_states()
+        assert np.max(np.abs(np.linalg.norm(psi, axis=1) - 1.0)) <= 1e-12
+        e.close()
+    assert abs(vals[1] - vals[0]) <= 1e-12

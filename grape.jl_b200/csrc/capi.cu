@@ -256,6 +256,12 @@ int small_setup(H* h, const grape_b200_problem* d) {
                 }
             }
             if (real) {
+                // series tables of the real-symmetric kernels: economised polynomial (default) or Taylor (GRAPE_B200_ECON=0);
+                // constant memory is per device and process-wide: handles created with different settings must not be mixed
+                const char* ee = getenv("GRAPE_B200_ECON");
+                if (sym_tables_upload(!(ee && atoi(ee) == 0)) != cudaSuccess) { h->err = "cudaMemcpyToSymbol failed (series tables)"; return GRAPE_B200_ECUDA; }
+            }
+            if (real) {
                 std::vector<double> rb((size_t)NN * G);
                 for (int g = 0; g < G; ++g)
                     for (int i = 0; i < N; ++i)

@@ -28,23 +28,58 @@
 // right behind it with run_if = notfast, does the work.
 #pragma once
 #include "small_seg.cuh"
+#include "econ.cuh"
+#include <algorithm>
 
-// theta <= SYM_TH[m]  <=>  theta^m / m! <= 2e-17 (vec_plan's criterion), m = 2..8
-__constant__ double c_sym_th[SEG_MMAX + 1] = {0.0, 0.0, 6.324548995781438e-09, 4.932419216236795e-06,
-                                              0.00014801641288189615, 0.001191356706809193, 0.004932419216236793,
-                                              0.013910766804023767, 0.030783527232167155};
-
-struct KappaTable {
-    double v[SEG_MMAX + 1][SEG_MMAX];
-    constexpr KappaTable() : v() {
-        double fact[SEG_MMAX + 1] = {};
-        fact[0] = 1.0;
-        for (int j = 1; j <= SEG_MMAX; ++j) fact[j] = fact[j - 1] * (double)j;
-        for (int a = 0; a <= SEG_MMAX; ++a)
-            for (int b = 0; b < SEG_MMAX; ++b) v[a][b] = 1.0 / ((double)(a + b + 1) * fact[a] * fact[b]);
-    }
+// Series tables of the real-symmetric kernels, filled by sym_tables_upload() when a handle is set up:
+//   * Taylor (GRAPE_B200_ECON=0): th[m] = the largest theta with theta^m / m! <= 2e-17 (vec_plan's criterion), g = 1;
+//   * economised (default; econ.cuh): the Chebyshev-cut polynomial p_m of exp(-i x) on [-th[m], th[m]] in the monomial
+//     basis -- one to two orders fewer for the same 1e-17 (C3: m = 6 instead of 7 in the gradient step, and a degree-6
+//     propagator polynomial instead of degree 7 in the formation).  The generators of this file are real symmetric,
+//     so the spectrum of Hs lies in [-||Hs||_1, ||Hs||_1].
+// ginv[m][a] = g[m][a] / a!;  kap[m][a][b] = g[m][a+b+1] / ((a+b+1) a! b!): the derivative of p_m(X) = sum_j g_j X^j / j!
+// is sum_j g_j / j! sum_{a+b=j-1} X^a dX X^b.
+constexpr int SYM_NCLS = 6;   // propagator classes of the formation kernels: degree 3, 5, 6, 8, 12, 16
+struct SymTab {
+    double th[SEG_MMAX + 1];
+    double ginv[SEG_MMAX + 1][SEG_MMAX + 1];
+    double kap[SEG_MMAX + 1][SEG_MMAX + 1][SEG_MMAX];
+    double fth[SYM_NCLS];        // radius of class c
+    double cc[SYM_NCLS][9];      // cos(x)   ~ sum_i cc[i] x^(2i),  i <= degree / 2
+    double sc[SYM_NCLS][9];      // sin(x)/x ~ sum_i sc[i] x^(2i),  i <= (degree - 1) / 2
 };
-__constant__ KappaTable c_kappa = KappaTable();
+__constant__ SymTab c_sym;
+constexpr int SYM_CLS_DEG[SYM_NCLS] = {3, 5, 6, 8, 12, 16};
+
+inline cudaError_t sym_tables_upload(bool econ) {
+    static SymTab tab;
+    memset(&tab, 0, sizeof tab);
+    const EconTab& et = econ_table();
+    long double fact[ECON_MAXM + 2];
+    fact[0] = 1.0L;
+    for (int j = 1; j <= ECON_MAXM + 1; ++j) fact[j] = fact[j - 1] * j;
+    for (int m = 2; m <= SEG_MMAX; ++m) {
+        // Taylor radius: theta^m / m! <= 2e-17
+        tab.th[m] = econ ? et.theta[m] : (double)powl(2e-17L * fact[m], 1.0L / m) * (1.0 - 1e-15);
+        for (int a = 0; a <= m; ++a) tab.ginv[m][a] = (double)((econ ? (long double)et.g[m][a] : 1.0L) / fact[a]);
+        for (int a = 0; a <= SEG_MMAX; ++a)
+            for (int b = 0; b < SEG_MMAX; ++b) {
+                const int j = a + b + 1;
+                const long double g = (econ && j <= m) ? (long double)et.g[m][j] : 1.0L;
+                tab.kap[m][a][b] = (double)(g / ((long double)j * fact[a] * fact[b]));
+            }
+    }
+    for (int c = 0; c < SYM_NCLS; ++c) {
+        const int m = SYM_CLS_DEG[c];
+        // Taylor radius of degree m: first dropped term theta^(m+1) / (m+1)! <= 1e-17
+        tab.fth[c] = econ ? et.theta[m] : std::min(1.0, (double)powl(1e-17L * fact[m + 1], 1.0L / (m + 1)) * (1.0 - 1e-15));
+        for (int j = 0; j <= m; ++j) {
+            const long double v = (econ ? (long double)et.g[m][j] : 1.0L) / fact[j] * (((j / 2) & 1) ? -1.0L : 1.0L);
+            if (j & 1) tab.sc[c][j / 2] = (double)v; else tab.cc[c][j / 2] = (double)v;
+        }
+    }
+    return cudaMemcpyToSymbol(c_sym, &tab, sizeof tab);
+}
 
 // C = A*B, real N x N row-major in registers
 template <int N>
@@ -80,7 +115,23 @@ GB_D cplx rot_i(cplx w, int r) {
     }
 }
 
-// Hs (unscaled: H0 + sum_l a_l Hc_l of generator g at step n) and its 1-norm
+// Upper bound of the spectral radius of a real symmetric matrix: min(1-norm, Frobenius norm).  Neither dominates (a
+// diagonal matrix: 1-norm exact, Frobenius up to sqrt(N) above; the Lambda system of C3: Frobenius 0.0065 where the
+// 1-norm gives 0.0091, which decides between 5 and 6 orders per gradient step).
+template <int N>
+GB_D double sym_radius_bound(const double (&Hs)[N * N]) {
+    double n1 = 0.0, f2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { s += fabs(Hs[i * N + j]); f2 = fma(Hs[i * N + j], Hs[i * N + j], f2); }
+        n1 = fmax(n1, s);
+    }
+    return fmin(n1, sqrt(f2) * (1.0 + 1e-14));
+}
+
+// Hs (unscaled: H0 + sum_l a_l Hc_l of generator g at step n) and the bound of its spectral radius
 template <int N>
 GB_D double sym_form_H(const DevP& p, const SegArgs& a, int g, int n, double (&Hs)[N * N]) {
     constexpr int NN = N * N;
@@ -93,15 +144,7 @@ GB_D double sym_form_H(const DevP& p, const SegArgs& a, int g, int n, double (&H
 #pragma unroll
         for (int c = 0; c < NN; ++c) Hs[c] = fma(am, __ldg(&a.Hcr[((size_t)l * NN + c) * G + g]), Hs[c]);
     }
-    double nrm = 0.0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
-        nrm = fmax(nrm, s);
-    }
-    return nrm;
+    return sym_radius_bound<N>(Hs);
 }
 
 // ---------------------------------------------------------------------------
@@ -120,7 +163,7 @@ __global__ void __launch_bounds__(128) small_formseg_sym(DevP p, SegArgs a) {
         const double dt = p.tlist[n + 1] - p.tlist[n];
         double Hs[NN];
         const double theta = dt * sym_form_H<N>(p, a, g, n, Hs);
-        if (theta > c_sym_th[SEG_MMAX]) *a.notfast = 1;   // the gradient kernel of this file cannot serve this step
+        if (theta > c_sym.th[SEG_MMAX]) *a.notfast = 1;   // the gradient kernel of this file cannot serve this step
         int degree, s;
         exp_plan(theta, degree, s);
         const double sc = s > 0 ? dt * ldexp(1.0, -s) : dt;
@@ -203,7 +246,7 @@ GB_D void sym_step(const double (&Hs)[N * N], cplx (&psi)[N], cplx (&chi)[N], do
 #pragma unroll
     for (int b = 0; b < M; ++b)
 #pragma unroll
-        for (int i = 0; i < N; ++i) e[b][i] = cscale(w[i], c_kappa.v[0][b]);
+        for (int i = 0; i < N; ++i) e[b][i] = cscale(w[i], c_sym.kap[M][0][b]);
 #pragma unroll
     for (int aa = 1; aa <= M; ++aa) {
         cplx nw[N];
@@ -211,12 +254,12 @@ GB_D void sym_step(const double (&Hs)[N * N], cplx (&psi)[N], cplx (&chi)[N], do
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             w[i] = nw[i];
-            cfmar(ap[i], c_invfact[aa], rot_i(nw[i], aa));
+            cfmar(ap[i], c_sym.ginv[M][aa], rot_i(nw[i], aa));
         }
 #pragma unroll
         for (int b = 0; b < M - aa; ++b)
 #pragma unroll
-            for (int i = 0; i < N; ++i) cfmar(e[b][i], c_kappa.v[aa][b], rot_i(nw[i], aa));
+            for (int i = 0; i < N; ++i) cfmar(e[b][i], c_sym.kap[M][aa][b], rot_i(nw[i], aa));
     }
     cplx x[N], ac[N];
 #pragma unroll
@@ -241,7 +284,7 @@ GB_D void sym_step(const double (&Hs)[N * N], cplx (&psi)[N], cplx (&chi)[N], do
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             x[i] = nx[i];
-            cfmar(ac[i], c_invfact[b + 1], rot_i(nx[i], b + 1));
+            cfmar(ac[i], c_sym.ginv[M][b + 1], rot_i(nx[i], b + 1));
         }
     }
 #pragma unroll
@@ -285,7 +328,7 @@ __global__ void __launch_bounds__(128, MINB) small_seggrad_sym(DevP p, SegArgs a
         const double theta = dt * sym_form_H<N>(p, a, g, nn, Hs);
         int m = 2;
 #pragma unroll
-        for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;
+        for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym.th[j] ? j + 1 : m;
         m = __reduce_max_sync(0xffffffffu, m);   // more orders never hurt: one uniform branch per warp
 #pragma unroll
         for (int c = 0; c < NN; ++c) Hs[c] *= dt;
@@ -359,15 +402,7 @@ GB_D double sym_form_H_amps(const double* sH, const double (&am)[LT > 0 ? LT : 1
     for (int l = 0; l < LT; ++l)
 #pragma unroll
         for (int c = 0; c < NN; ++c) Hs[c] = fma(am[l], sH[(NN + l * NN + c) * BD + t], Hs[c]);
-    double nrm = 0.0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
-        nrm = fmax(nrm, s);
-    }
-    return nrm;
+    return sym_radius_bound<N>(Hs);
 }
 template <int N, int LT, int BD = SYM_BD>
 GB_D double sym_form_H_staged(const DevP& p, const double* sH, int L, int n, double (&Hs)[N * N]) {
@@ -391,70 +426,88 @@ GB_D double sym_form_H_staged(const DevP& p, const double* sH, int L, int n, dou
             for (int c = 0; c < NN; ++c) Hs[c] = fma(am, sH[(NN + l * NN + c) * BD + t], Hs[c]);
         }
     }
-    double nrm = 0.0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
-        nrm = fmax(nrm, s);
-    }
-    return nrm;
+    return sym_radius_bound<N>(Hs);
 }
 
-// cos(Hs) and Sp = sin(Hs)/Hs as Horner polynomials in Q = Hs^2 with D2 + 1 terms each; D2 is a template parameter
-// (the four degree classes of exp_plan: 3, 7, 11, 15 -> D2 = 1, 3, 5, 7), so the coefficients are immediates and the
-// loop unrolls (the run-time loop cost 15 % of the formation kernel's instructions in IMAD / LDC / branches)
-template <int N, int D2>
+// C = A B for two COMMUTING symmetric matrices (polynomials in the same Hs): the product is symmetric, only the upper
+// triangle is computed (N = 3: 6 dot products instead of 9) and both halves hold the same rounded value
+template <int N>
+GB_D void rm_mm_sym(double (&C)[N * N], const double (&A)[N * N], const double (&B)[N * N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = i; j < N; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) acc = fma(A[i * N + k], B[k * N + j], acc);
+            C[i * N + j] = acc;
+            C[j * N + i] = acc;
+        }
+}
+
+// Cm = cos(Hs) and Sp = sin(Hs)/Hs as Horner polynomials in Q = Hs^2: the even / odd halves of the degree-DEG
+// polynomial of class CLS (c_sym: Chebyshev-cut or Taylor).  CLS is a template parameter, so the coefficients are
+// constant-bank operands and the loops unroll (a run-time loop cost 15 % of the formation kernel's instructions).
+template <int N, int CLS>
 GB_D void sym_cos_sinc_poly(const double (&Q)[N * N], double (&Cm)[N * N], double (&Sp)[N * N]) {
     constexpr int NN = N * N;
-    {
-        constexpr double sg = (D2 & 1) ? -1.0 : 1.0;
-        const double c1 = sg * c_invfact[2 * D2], c0 = -sg * c_invfact[2 * D2 - 2];
-        const double s1 = sg * c_invfact[2 * D2 + 1], s0 = -sg * c_invfact[2 * D2 - 1];
+    constexpr int DEG = SYM_CLS_DEG[CLS], DC = DEG / 2, DS = (DEG - 1) / 2;   // DC = DS (odd degree) or DS + 1 (even)
+    static_assert(DS >= 1 && (DC == DS || DC == DS + 1), "degree >= 3");
 #pragma unroll
-        for (int c = 0; c < NN; ++c) { Cm[c] = c1 * Q[c]; Sp[c] = s1 * Q[c]; }
+    for (int c = 0; c < NN; ++c) { Cm[c] = c_sym.cc[CLS][DC] * Q[c]; Sp[c] = c_sym.sc[CLS][DS] * Q[c]; }
 #pragma unroll
-        for (int i = 0; i < N; ++i) { Cm[i * N + i] += c0; Sp[i * N + i] += s0; }
+    for (int i = 0; i < N; ++i) { Cm[i * N + i] += c_sym.cc[CLS][DC - 1]; Sp[i * N + i] += c_sym.sc[CLS][DS - 1]; }
+    if (DC > DS) {   // even degree: the cosine has one term more -- one product on its own, then both series in step
+        double T1[NN];
+        rm_mm_sym<N>(T1, Q, Cm);
+#pragma unroll
+        for (int c = 0; c < NN; ++c) Cm[c] = T1[c];
+#pragma unroll
+        for (int i = 0; i < N; ++i) Cm[i * N + i] += c_sym.cc[CLS][DC - 2];
     }
 #pragma unroll
-    for (int j = D2 - 2; j >= 0; --j) {
-        const double sg = (j & 1) ? -1.0 : 1.0;
-        const double cj = sg * c_invfact[2 * j], sj = sg * c_invfact[2 * j + 1];
+    for (int j = DS - 2; j >= 0; --j) {
         double T1[NN], T2[NN];
-        rm_mm<N>(T1, Q, Cm);
-        rm_mm<N>(T2, Q, Sp);
+        rm_mm_sym<N>(T1, Q, Cm);
+        rm_mm_sym<N>(T2, Q, Sp);
 #pragma unroll
         for (int c = 0; c < NN; ++c) { Cm[c] = T1[c]; Sp[c] = T2[c]; }
 #pragma unroll
-        for (int i = 0; i < N; ++i) { Cm[i * N + i] += cj; Sp[i * N + i] += sj; }
+        for (int i = 0; i < N; ++i) { Cm[i * N + i] += c_sym.cc[CLS][j]; Sp[i * N + i] += c_sym.sc[CLS][j]; }
     }
 }
 
-// U_n = cos(Hs) - i sin(Hs) of one step (Hs unscaled generator, theta = dt * ||Hs||_1), as in small_formseg_sym
+// U_n = cos(Hs) - i sin(Hs) of one step (Hs unscaled generator, theta >= dt * its spectral radius: sym_radius_bound)
 template <int N>
 GB_D void sym_cos_sin(double (&Hs)[N * N], double dt, double theta, double (&Cm)[N * N], double (&Sm)[N * N]) {
     constexpr int NN = N * N;
-    int degree, s;
-    exp_plan(theta, degree, s);
+    int cls = 0, s = 0;
+#pragma unroll
+    for (int c = 0; c < SYM_NCLS - 1; ++c) cls = theta > c_sym.fth[c] ? c + 1 : cls;
+    {
+        double t = theta;
+        while (t > c_sym.fth[SYM_NCLS - 1] && s < 60) { t *= 0.5; ++s; }   // scaling and squaring beyond the top class
+    }
     const double sc = s > 0 ? dt * ldexp(1.0, -s) : dt;
 #pragma unroll
     for (int c = 0; c < NN; ++c) Hs[c] *= sc;
     double Q[NN];
-    rm_mm<N>(Q, Hs, Hs);
+    rm_mm_sym<N>(Q, Hs, Hs);
     double Sp[NN];
-    switch (degree) {   // same operations in the same order as the run-time Horner loop of small_formseg_sym
-        case 3: sym_cos_sinc_poly<N, 1>(Q, Cm, Sp); break;
-        case 7: sym_cos_sinc_poly<N, 3>(Q, Cm, Sp); break;
-        case 11: sym_cos_sinc_poly<N, 5>(Q, Cm, Sp); break;
-        default: sym_cos_sinc_poly<N, 7>(Q, Cm, Sp); break;
+    switch (cls) {
+        case 0: sym_cos_sinc_poly<N, 0>(Q, Cm, Sp); break;
+        case 1: sym_cos_sinc_poly<N, 1>(Q, Cm, Sp); break;
+        case 2: sym_cos_sinc_poly<N, 2>(Q, Cm, Sp); break;
+        case 3: sym_cos_sinc_poly<N, 3>(Q, Cm, Sp); break;
+        case 4: sym_cos_sinc_poly<N, 4>(Q, Cm, Sp); break;
+        default: sym_cos_sinc_poly<N, 5>(Q, Cm, Sp); break;
     }
-    rm_mm<N>(Sm, Hs, Sp);
+    rm_mm_sym<N>(Sm, Hs, Sp);
     for (int t = 0; t < s; ++t) {   // (C - iS)^2 = (C^2 - S^2) - i (2 S C)
         double T1[NN], T2[NN], T3[NN];
-        rm_mm<N>(T1, Cm, Cm);
-        rm_mm<N>(T2, Sm, Sm);
-        rm_mm<N>(T3, Sm, Cm);
+        rm_mm_sym<N>(T1, Cm, Cm);
+        rm_mm_sym<N>(T2, Sm, Sm);
+        rm_mm_sym<N>(T3, Sm, Cm);
 #pragma unroll
         for (int c = 0; c < NN; ++c) { Cm[c] = T1[c] - T2[c]; Sm[c] = 2.0 * T3[c]; }
     }
@@ -683,11 +736,11 @@ __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a
         }
         int m = 2;
 #pragma unroll
-        for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym_th[j] ? j + 1 : m;
+        for (int j = 2; j < SEG_MMAX; ++j) m = theta > c_sym.th[j] ? j + 1 : m;
         // steps beyond 8 orders (||H dt||_1 > 0.0308): nsub equal sub-steps of 8 orders each -- the integral
         // M = int_0^1 Psi(s) chi(s)^dagger ds of the step is the mean of the sub-steps' integrals.  Decided per warp and
         // per step (round 1 sent the WHOLE call to the 1.8x slower complex kernel if one step anywhere was ineligible).
-        int nsub = theta > c_sym_th[SEG_MMAX] ? (int)ceil(theta / c_sym_th[SEG_MMAX]) : 1;
+        int nsub = theta > c_sym.th[SEG_MMAX] ? (int)ceil(theta / c_sym.th[SEG_MMAX]) : 1;
         m = __reduce_max_sync(0xffffffffu, m);   // more orders never hurt: one uniform branch per warp
         nsub = __reduce_max_sync(0xffffffffu, nsub);
 #pragma unroll
@@ -824,14 +877,7 @@ __global__ void __launch_bounds__(32 * SCAN_MAXW, 3) small_formscan_sym(DevP p, 
         } else {
             for (int l = 0; l < L; ++l) add_control(l);
         }
-        double nrm = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            double s = 0.0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) s += fabs(Hs[i * N + j]);
-            nrm = fmax(nrm, s);
-        }
+        const double nrm = sym_radius_bound<N>(Hs);
         double Cm[NN], Sm[NN];
         sym_cos_sin<N>(Hs, dt, dt * nrm, Cm, Sm);
         if (n == n0) {

@@ -91,7 +91,8 @@ def test_lane_mapping_and_functionals(lib_built, K):
 
 
 def test_ineligible_steps_fall_back_on_the_device(lib_built):
-    """ROUND-1 kernels (GRAPE_B200_SYM_V=1): a step with ||H dt|| > 0.0308 (more than 8 orders / sub-stepping) switches
+    """ROUND-1 kernels (GRAPE_B200_SYM_V=1): a step with ||H dt|| > 0.099 (economised polynomial; Taylor: 0.0308 -- more
+    than 8 orders / sub-stepping) switches
     the whole call to the general Hermitian kernel on the device; the flag follows the pulses call by call"""
     p, eps = configs.random_problem(K=6, N=3, L=2, NT=25, seed=431, real=True, functional=gb.SM)
     check(p, eps, schedule=2, GRAPE_B200_SYM_V=1)[0].close()              # dt ~ 0.05, ||H|| ~ 3
@@ -99,7 +100,7 @@ def test_ineligible_steps_fall_back_on_the_device(lib_built):
     e = engine(p, GRAPE_B200_SYM_V=1)
     op = go.from_problem(p)
     G = np.zeros_like(eps)
-    for amp, sched in ((1.0, 3), (40.0, 2), (0.5, 3), (40.0, 2), (1.0, 3)):
+    for amp, sched in ((1.0, 3), (150.0, 2), (0.5, 3), (150.0, 2), (1.0, 3)):
         x = eps * amp
         ref = go.evaluate_gradient(op, x)
         J = e.evaluate_gradient(G, x)
@@ -212,3 +213,33 @@ def test_c3_full_size_real_vs_hermitian_schedule(lib_built):
     es.evaluate_gradient(Gs, eps)
     assert np.max(np.abs(Gs - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
     es.close()
+
+
+@pytest.mark.parametrize("econ", [1, 0])
+@pytest.mark.parametrize("theta", [3e-4, 1e-3, 1e-2, 0.05, 0.3, 0.8, 2.5])
+def test_propagator_classes_economised_and_taylor(lib_built, theta, econ):
+    """||H dt|| swept over the five polynomial classes of the formation kernels (degree 4, 6, 8, 12, 16) and into scaling
+    and squaring, with the Chebyshev-cut coefficients (default) and the Taylor coefficients (GRAPE_B200_ECON=0): both
+    match the oracle's exact exponential at 1e-10 (csrc/small_sym.cuh sym_tables_upload, csrc/econ.cuh)."""
+    for scan in (1, 0):
+        p, eps = configs.random_problem(K=7, N=3, L=2, NT=23, seed=470, real=True, uniform=True, functional=gb.SM)
+        nrm = max(np.abs(p.H0[g] + sum(abs(eps.reshape(p.L, p.NT)[l]).max() * np.abs(p.Hc[g, l]) for l in range(p.L))).sum(0).max()
+                  for g in range(p.H0.shape[0]))
+        p.tlist[:] = p.tlist * (theta / (nrm * 0.05))
+        check(p, eps, GRAPE_B200_ECON=econ, GRAPE_B200_SEG_SCAN=scan)[0].close()
+
+
+def test_economised_and_taylor_series_agree_on_c3_shard(lib_built):
+    """a 256-trajectory shard of C3, all 1000 steps: the economised polynomial (degree 6 per gradient step) and the
+    Taylor series (degree 7) give the same J and gradient to 1e-12"""
+    p, eps = configs.c3_ensemble(n_delta=16, n_amp=16)
+    out = {}
+    for econ in (1, 0):
+        e = engine(p, GRAPE_B200_ECON=econ)
+        G = np.zeros_like(eps)
+        out[econ] = (e.evaluate_gradient(G, eps), G)
+        assert e.small_schedule() == 3
+        e.close()
+    scale = np.max(np.abs(out[0][1]))
+    assert abs(out[1][0] - out[0][0]) <= 1e-12 * max(1.0, abs(out[0][0]))
+    assert np.max(np.abs(out[1][1] - out[0][1])) <= 1e-12 * scale

@@ -521,10 +521,11 @@ void seg_grad_t(H* h) {
         } else {
             // staged kernels: every step is served (sub-stepping inside), no second launch
             // (two-warp blocks for under-filled launches were measured: no difference, profiles/r2_s13_c3_sweep.txt)
-            if (h->p.L == 1) small_seggrad_sym2<NS, 1><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
-            else if (h->p.L == 2 && h->sym_occ == 4) small_seggrad_sym2<NS, 2, 4><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: 128 registers
-            else if (h->p.L == 2 && h->sym_occ == 5) small_seggrad_sym2<NS, 2, 3, SYM_BD, true><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);   // A/B: prefetch of the next step's pulse values
-            else if (h->p.L == 2) small_seggrad_sym2<NS, 2><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            // one or two controls: 128 registers (16 warps / SM), orders 7 and 8 out of line (profiles/r2_s19_c3_variants.txt:
+            // 0.311 ms against 0.322 ms with 168 registers and all orders inline; GRAPE_B200_SYM_OCC=10 selects the latter)
+            if (h->p.L == 1) small_seggrad_sym2<NS, 1, 4, SYM_BD, false, 6><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            else if (h->p.L == 2 && h->sym_occ == 10) small_seggrad_sym2<NS, 2, 3, SYM_BD, false, 8><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
+            else if (h->p.L == 2) small_seggrad_sym2<NS, 2, 4, SYM_BD, false, 6><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             else small_seggrad_sym2<NS, 0><<<blocks, SYM_BD, sm, h->stream>>>(h->p, a);
             h->launches++;
             return;

@@ -513,8 +513,29 @@ GB_D void sym_cos_sin(double (&Hs)[N * N], double dt, double theta, double (&Cm)
     }
 }
 
-template <int N, int LT>
-__global__ void __launch_bounds__(SYM_BD, 3) small_formseg_sym2(DevP p, SegArgs a) {
+// B <- (C - iS) A on split real / imaginary arrays (four real products)
+template <int N>
+GB_D void sym_apply_U(const double (&Cm)[N * N], const double (&Sm)[N * N], const double (&Ar)[N * N], const double (&Ai)[N * N],
+                      double (&Br)[N * N], double (&Bi)[N * N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double ar = 0.0, ai = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                ar = fma(Cm[i * N + k], Ar[k * N + j], ar);
+                ar = fma(Sm[i * N + k], Ai[k * N + j], ar);
+                ai = fma(Cm[i * N + k], Ai[k * N + j], ai);
+                ai = fma(-Sm[i * N + k], Ar[k * N + j], ai);
+            }
+            Br[i * N + j] = ar;
+            Bi[i * N + j] = ai;
+        }
+}
+
+template <int N, int LT, int MINB = 3>
+__global__ void __launch_bounds__(SYM_BD, MINB) small_formseg_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -524,32 +545,32 @@ __global__ void __launch_bounds__(SYM_BD, 3) small_formseg_sym2(DevP p, SegArgs 
     const int n0 = seg * a.S, n1 = min(NT, n0 + a.S);
     sym_stage<N>(p, a, g, L, sH);
     double Pr[NN], Pi[NN];
-    for (int n = n0; n < n1; ++n) {
+    auto step_U = [&](int n, double (&Cm)[NN], double (&Sm)[NN]) {
         const double dt = p.tlist[n + 1] - p.tlist[n];
         double Hs[NN];
         const double theta = dt * sym_form_H_staged<N, LT>(p, sH, L, n, Hs);
-        double Cm[NN], Sm[NN];
         sym_cos_sin<N>(Hs, dt, theta, Cm, Sm);
-        if (n == n0) {
+    };
+    {
+        double Cm[NN], Sm[NN];
+        step_U(n0, Cm, Sm);
 #pragma unroll
-            for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
-        } else {   // (C - iS)(Pr + i Pi)
-            double Tr[NN], Ti[NN];
-#pragma unroll
-            for (int i = 0; i < N; ++i)
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double ar = 0.0, ai = 0.0;
-#pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        ar = fma(Cm[i * N + k], Pr[k * N + j], ar);
-                        ar = fma(Sm[i * N + k], Pi[k * N + j], ar);
-                        ai = fma(Cm[i * N + k], Pi[k * N + j], ai);
-                        ai = fma(-Sm[i * N + k], Pr[k * N + j], ai);
-                    }
-                    Tr[i * N + j] = ar;
-                    Ti[i * N + j] = ai;
-                }
+        for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
+    }
+    // two steps per trip, P -> T -> P: the product lands where the next step reads it (a one-step loop copied the 2 N^2
+    // doubles back every step: 36 of the 430 instructions per step were register moves, ncu source page r2_s19)
+    for (int n = n0 + 1; n < n1; n += 2) {
+        double Tr[NN], Ti[NN];
+        {
+            double Cm[NN], Sm[NN];
+            step_U(n, Cm, Sm);
+            sym_apply_U<N>(Cm, Sm, Pr, Pi, Tr, Ti);
+        }
+        if (n + 1 < n1) {
+            double Cm[NN], Sm[NN];
+            step_U(n + 1, Cm, Sm);
+            sym_apply_U<N>(Cm, Sm, Tr, Ti, Pr, Pi);
+        } else {
 #pragma unroll
             for (int c = 0; c < NN; ++c) { Pr[c] = Tr[c]; Pi[c] = Ti[c]; }
         }
@@ -574,9 +595,20 @@ __device__ __noinline__ void sym_step_sub(double (&Hs)[N * N], cplx (&psi)[N], c
     }
 }
 
-// BD / MINB: 128 threads, 3 blocks per SM (168 registers, 12 warps).  Two-warp blocks (BD = 64, MINB = 6) for
-// under-filled launches and a 128-register build (MINB = 4) were measured and are not used (no gain / 8 % slower).
-template <int N, int LT, int MINB = 3, int BD = SYM_BD, bool PF = false>
+// orders above the inline limit MI of the gradient kernel (out of line like the sub-stepped steps: the register budget
+// of the kernel is then set by sym_step<N, MI>, not by the rarely needed sym_step<N, 8>)
+template <int N>
+__device__ __noinline__ void sym_step_hi(const double (&Hs)[N * N], cplx (&psi)[N], cplx (&chi)[N], double (&IM)[N * N], int m) {
+    if (m <= 7) sym_step<N, 7>(Hs, psi, chi, IM);
+    else sym_step<N, 8>(Hs, psi, chi, IM);
+}
+
+// BD / MINB / MI: 128 threads; launched with MINB = 4 (128 registers, 16 warps / SM) and MI = 6 (orders 7, 8 out of
+// line) for one or two controls, MINB = 3 (168 registers) and all orders inline for a run-time number of controls.
+// Measured on C3 (profiles/r2_s18_c3_variants.txt, r2_s19_c3_variants.txt): 128 registers with all orders inline is 8 %
+// slower than 168 (spills), with MI = 6 it is 3 % faster; two-warp blocks (BD = 64) and the pulse-value prefetch (PF)
+// gave nothing; a 128-register build of the formation kernel is 3 % slower.
+template <int N, int LT, int MINB = 3, int BD = SYM_BD, bool PF = false, int MI = 8>
 __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a) {
     constexpr int NN = N * N;
     extern __shared__ double sH[];
@@ -746,16 +778,28 @@ __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a
 #pragma unroll
         for (int c = 0; c < NN; ++c) Hs[c] *= dt;
         double IM[NN];
-        if (nsub == 1) {
+        if (nsub == 1 && m <= MI) {
             switch (m) {
                 case 2: sym_step<N, 2>(Hs, psi, chi, IM); break;
                 case 3: sym_step<N, 3>(Hs, psi, chi, IM); break;
                 case 4: sym_step<N, 4>(Hs, psi, chi, IM); break;
                 case 5: sym_step<N, 5>(Hs, psi, chi, IM); break;
-                case 6: sym_step<N, 6>(Hs, psi, chi, IM); break;
-                case 7: sym_step<N, 7>(Hs, psi, chi, IM); break;
-                default: sym_step<N, 8>(Hs, psi, chi, IM); break;
+                case 6: sym_step<N, MI >= 6 ? 6 : 2>(Hs, psi, chi, IM); break;
+                case 7: sym_step<N, MI >= 7 ? 7 : 2>(Hs, psi, chi, IM); break;
+                default: sym_step<N, MI >= 8 ? 8 : 2>(Hs, psi, chi, IM); break;
             }
+        } else if (nsub == 1) {   // m > MI
+            double Hs2[NN], IM2[NN];
+            cplx psi2[N], chi2[N];
+#pragma unroll
+            for (int c = 0; c < NN; ++c) Hs2[c] = Hs[c];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { psi2[i] = psi[i]; chi2[i] = chi[i]; }
+            sym_step_hi<N>(Hs2, psi2, chi2, IM2, m);
+#pragma unroll
+            for (int c = 0; c < NN; ++c) IM[c] = IM2[c];
+#pragma unroll
+            for (int i = 0; i < N; ++i) { psi[i] = psi2[i]; chi[i] = chi2[i]; }
         } else {   // copies: only they live in local memory for the out-of-line call
             double Hs2[NN], IM2[NN];
             cplx psi2[N], chi2[N];
@@ -769,12 +813,16 @@ __global__ void __launch_bounds__(BD, MINB) small_seggrad_sym2(DevP p, SegArgs a
 #pragma unroll
             for (int i = 0; i < N; ++i) { psi[i] = psi2[i]; chi[i] = chi2[i]; }
         }
+        // The control operators are read from shared memory twice per step (H formation above, the traces below).  Without
+        // the volatile read the compiler keeps the 9 L values of the first read alive across sym_step -- in local memory:
+        // 20 STL.64 + 20 LDL.64 per step (ncu source page, profiles/r2_s18_ncu_c3_source.csv) -- instead of re-reading.
+        const volatile double* const sHv = sH;
         auto trace = [&](int l) {
             double sl = dt * rho;
             if (p.dshape) sl *= p.dshape[l * NT + nn];
             double acc = 0.0;
 #pragma unroll
-            for (int c = 0; c < NN; ++c) acc = fma(sH[(NN + l * NN + c) * BD + threadIdx.x], IM[c], acc);
+            for (int c = 0; c < NN; ++c) acc = fma(sHv[(NN + l * NN + c) * BD + threadIdx.x], IM[c], acc);
             return act ? sl * acc : 0.0;
         };
         if (LT > 0) {

@@ -1287,7 +1287,11 @@ inline int dense_setup(DensePlan& dp, DevP& p, const grape_b200_problem* desc, s
         // economised polynomial instead of the Taylor series on the Krylov-form schedule (GRAPE_B200_ECON=0: Taylor)
         const char* e = getenv("GRAPE_B200_ECON");
         d.econ = d.herm && !(e && atoi(e) == 0);
-        if (cudaMemcpyToSymbol(c_econ, &econ_table(), sizeof(EconTab)) != cudaSuccess) { err = "cudaMemcpyToSymbol failed (economised-polynomial table)"; return GRAPE_B200_ECUDA; }
+        static bool uploaded[64];   // the table does not depend on the problem: once per device
+        if (!(dev >= 0 && dev < 64 && uploaded[dev])) {
+            if (cudaMemcpyToSymbol(c_econ, &econ_table(), sizeof(EconTab)) != cudaSuccess) { err = "cudaMemcpyToSymbol failed (economised-polynomial table)"; return GRAPE_B200_ECUDA; }
+            if (dev >= 0 && dev < 64) uploaded[dev] = true;
+        }
     }
     if (p.gb_kind) {
         std::vector<double> dm(2 * hplane, 0.0);

@@ -52,6 +52,12 @@ __constant__ SymTab c_sym;
 constexpr int SYM_CLS_DEG[SYM_NCLS] = {3, 5, 6, 8, 12, 16};
 
 inline cudaError_t sym_tables_upload(bool econ) {
+    // once per device and setting: a second handle with the same setting must not rewrite the table under the kernels
+    // of the first one (constant memory is per device, shared by all handles of the process)
+    static int uploaded[64];   // 0: nothing, 1: Taylor, 2: economised
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && uploaded[dev] == (econ ? 2 : 1)) return cudaSuccess;
     static SymTab tab;
     memset(&tab, 0, sizeof tab);
     const EconTab& et = econ_table();
@@ -78,7 +84,9 @@ inline cudaError_t sym_tables_upload(bool econ) {
             if (j & 1) tab.sc[c][j / 2] = (double)v; else tab.cc[c][j / 2] = (double)v;
         }
     }
-    return cudaMemcpyToSymbol(c_sym, &tab, sizeof tab);
+    const cudaError_t e = cudaMemcpyToSymbol(c_sym, &tab, sizeof tab);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) uploaded[dev] = econ ? 2 : 1;
+    return e;
 }
 
 // C = A*B, real N x N row-major in registers
@@ -908,7 +916,7 @@ __global__ void __launch_bounds__(32 * SCAN_MAXW, 3) small_formscan_sym(DevP p, 
     for (int c = 0; c < NN; ++c) { Pr[c] = 0.0; Pi[c] = 0.0; }
 #pragma unroll
     for (int i = 0; i < N; ++i) Pr[i * N + i] = 1.0;               // lanes past the last segment carry the identity
-    for (int n = n0; n < n1; ++n) {
+    auto step_U = [&](int n, double (&Cm)[NN], double (&Sm)[NN]) {
         const double dt = p.tlist[n + 1] - p.tlist[n];
         double Hs[NN];
 #pragma unroll
@@ -926,28 +934,26 @@ __global__ void __launch_bounds__(32 * SCAN_MAXW, 3) small_formscan_sym(DevP p, 
             for (int l = 0; l < L; ++l) add_control(l);
         }
         const double nrm = sym_radius_bound<N>(Hs);
-        double Cm[NN], Sm[NN];
         sym_cos_sin<N>(Hs, dt, dt * nrm, Cm, Sm);
-        if (n == n0) {
+    };
+    if (n0 < n1) {
+        double Cm[NN], Sm[NN];
+        step_U(n0, Cm, Sm);
 #pragma unroll
-            for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
-        } else {   // (C - iS)(Pr + i Pi)
-            double Tr[NN], Ti[NN];
-#pragma unroll
-            for (int i = 0; i < N; ++i)
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double ar = 0.0, ai = 0.0;
-#pragma unroll
-                    for (int k = 0; k < N; ++k) {
-                        ar = fma(Cm[i * N + k], Pr[k * N + j], ar);
-                        ar = fma(Sm[i * N + k], Pi[k * N + j], ar);
-                        ai = fma(Cm[i * N + k], Pi[k * N + j], ai);
-                        ai = fma(-Sm[i * N + k], Pr[k * N + j], ai);
-                    }
-                    Tr[i * N + j] = ar;
-                    Ti[i * N + j] = ai;
-                }
+        for (int c = 0; c < NN; ++c) { Pr[c] = Cm[c]; Pi[c] = -Sm[c]; }
+    }
+    for (int n = n0 + 1; n < n1; n += 2) {   // two steps per trip, P -> T -> P (small_formseg_sym2)
+        double Tr[NN], Ti[NN];
+        {
+            double Cm[NN], Sm[NN];
+            step_U(n, Cm, Sm);
+            sym_apply_U<N>(Cm, Sm, Pr, Pi, Tr, Ti);
+        }
+        if (n + 1 < n1) {
+            double Cm[NN], Sm[NN];
+            step_U(n + 1, Cm, Sm);
+            sym_apply_U<N>(Cm, Sm, Tr, Ti, Pr, Pi);
+        } else {
 #pragma unroll
             for (int c = 0; c < NN; ++c) { Pr[c] = Tr[c]; Pi[c] = Ti[c]; }
         }

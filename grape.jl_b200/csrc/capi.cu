@@ -1010,7 +1010,7 @@ int grape_b200_create(const grape_b200_problem* d, grape_b200_handle** out) {
             rc = warp_setup(h->warp, p, d, h->dev_allocs, e);
             // time-segmented schedule unless a state running cost couples chi to Psi at every step
             h->wseg_on = !rc && p.gb_kind == 0 && d->path != GRAPE_B200_PATH_WARP_CHAIN;
-            if (h->wseg_on) rc = warp_seg_setup(h->wseg, h->warp, p, h->dev_allocs, e);
+            if (h->wseg_on) rc = warp_seg_setup(h->wseg, h->warp, p, d, h->dev_allocs, e);
             if (rc) h->err = e;
             break;
         }

@@ -272,3 +272,65 @@ def test_c3_full_size_hermitian_vs_general_schedule(lib_built):
         del os.environ["GRAPE_B200_SEG_HERM"]
     assert abs(J - J0) < 1e-13
     assert np.max(np.abs(G - G0)) <= 1e-12 * np.max(np.abs(G0))
+
+
+# ---- sub-warp path, Hermitian generators: scan schedule (csrc/warp_seg.cuh warp_segscan / warp_scan_bounds_*);
+# ---- GRAPE_B200_WSEG_SCAN=0 keeps the boundary chains
+@pytest.fixture
+def wscan(request):
+    old = os.environ.get("GRAPE_B200_WSEG_SCAN")
+    os.environ["GRAPE_B200_WSEG_SCAN"] = str(request.param)
+    yield request.param
+    if old is None:
+        del os.environ["GRAPE_B200_WSEG_SCAN"]
+    else:
+        os.environ["GRAPE_B200_WSEG_SCAN"] = old
+
+
+@pytest.mark.parametrize("wscan", [1, 0], indirect=True)
+@pytest.mark.parametrize("N,NT", [(5, 16), (6, 37), (9, 300), (16, 64), (17, 150), (32, 90)])
+def test_warp_scan_schedule_hermitian(lib_built, wscan, N, NT):
+    """prefix products over the segments by a scan, boundary states Psi = Q_seg Psi(0), chi = Q_seg Q_last^dagger chi(T)
+    (every P unitary): every sub-warp width, ragged last segment, two generators, shaped pulses, all three functionals"""
+    for fn in (gb.SM, gb.RE, gb.SS):
+        p, eps = configs.random_problem(K=5, N=N, L=2, NT=NT, seed=600 + N + fn, hermitian=True, shaped=True,
+                                        functional=fn, G=2, weights=np.linspace(0.5, 1.5, 5))
+        p.tlist[:] = p.tlist * (0.6 / np.sqrt(N))
+        check(p, eps)[0].close()
+
+
+@pytest.mark.parametrize("seg_len", [2, 3, 5], indirect=True)
+@pytest.mark.parametrize("N", [6, 20, 32])
+def test_warp_scan_more_segments_than_sub_warps(lib_built, seg_len, N):
+    """forced short segments: NSEG = 100 .. 150 > the 128 / 64 / 32 sub-warps of the scan block (looped levels)"""
+    p, eps = configs.random_problem(K=3, N=N, L=2, NT=300, seed=640 + N, hermitian=True, functional=gb.SM, G=1)
+    p.tlist[:] = p.tlist * (0.6 / np.sqrt(N))
+    check(p, eps)[0].close()
+
+
+def test_warp_scan_matches_chain_schedule_and_host_chi(lib_built):
+    p, eps = configs.c2_transmon(NT=500)
+    out = {}
+    for mode in (1, 0):
+        os.environ["GRAPE_B200_WSEG_SCAN"] = str(mode)
+        try:
+            e, J, G = run(p, eps)
+        finally:
+            del os.environ["GRAPE_B200_WSEG_SCAN"]
+        chi, rho = e.chi_states()
+        out[mode] = (J, G, chi, rho, e.stored_states(1))
+        e.close()
+    assert abs(out[1][0] - out[0][0]) <= 1e-13
+    assert np.max(np.abs(out[1][1] - out[0][1])) <= 1e-12 * np.max(np.abs(out[0][1]))
+    assert np.max(np.abs(out[1][2] - out[0][2])) <= 1e-12 and np.max(np.abs(out[1][3] - out[0][3])) <= 1e-12
+    assert np.max(np.abs(out[1][4] - out[0][4])) <= 1e-12
+    # host-supplied chi through the scan schedule
+    ref = go.evaluate_gradient(go.from_problem(p), eps)
+    ph, _ = configs.c2_transmon(NT=500, functional=gb.HOST)
+    eh = engine(ph)
+    eh.forward(eps)
+    tau = np.einsum("ki,ki->k", ph.tgt.conj(), eh.final_states())
+    Gp = np.zeros_like(eps)
+    eh.backward_chi((np.sum(tau) / ph.K ** 2) * ph.tgt, Gp)
+    assert np.max(np.abs(Gp - ref["G"])) <= RTOL * np.max(np.abs(ref["G"]))
+    eh.close()

@@ -19,13 +19,14 @@
 // levels of independent N x N products, one short kernel per level -- after which every boundary state is one or two
 // mat-vecs, independent of all the others:
 //     Psi_k(end of seg) = Q_seg Psi_k(0),   chi_k(end of seg) = Q_seg Q_last^dagger chi_k(T).
-// Without the chains short segments cost nothing extra: S = NT / 128 instead of sqrt(NT), so the segment products and
-// both fills are 16 instead of 45 dependent steps deep on C2.
+// Without the chains short segments only cost scan levels: S = NT / 256 instead of sqrt(NT), so the segment products
+// and both fills are 8 instead of 45 dependent steps deep on C2.
 struct WarpSegArgs {
     int S, NSEG;
     cplx* Pseg;   // [NSEG][G][N*N] row-major
     int scan;     // scan schedule (Hermitian generators)
     int pf;       // warp_segprod: propagators double-buffered through cp.async
+    int radix;    // factors per scan level (2 or 4)
     cplx* Qa;     // ping-pong buffers of the scan, same layout as Pseg
     cplx* Qb;
     const cplx* Q;   // where the prefix products end up (Pseg, Qa or Qb: fixed by the number of levels)
@@ -244,12 +245,14 @@ __global__ void __launch_bounds__(128) warp_seg_bwd(DevP p, WarpSegArgs a, const
 // ---------------------------------------------------------------------------
 // scan schedule
 // ---------------------------------------------------------------------------
-// one level of the inclusive prefix products over the segments (Kogge-Stone): x_seg <- x_seg x_{seg-off}, from `in`
-// to `out`; sub-warp per (g, seg) over the whole grid, both operands staged in shared memory.  One launch per level
-// (ceil(log2 NSEG) short kernels inside the call's CUDA graph): a single block per generator with operands in global
-// memory took 7 us per level on C2 (L2 round trips inside the product loop), a level launched grid-wide takes ~ 4.
+// one level of the inclusive prefix products over the segments (Kogge-Stone with radix R = 2 or 4):
+//     x_seg <- x_seg x_{seg-off} [x_{seg-2 off} x_{seg-3 off}],   off = 1, R, R^2, ..
+// from `in` to `out`; sub-warp per (g, seg) over the whole grid, operands staged in shared memory.  One launch per level
+// inside the call's CUDA graph.  Measured on C2 (profiles/r2_s23_*, r2_s24_*): one block per generator with operands in
+// global memory took 7 us per level (L2 round trips inside the product loop), a radix-2 level launched grid-wide 5 us --
+// mostly launch latency, hence radix 4: half the levels, three short products each.
 template <int W>
-__global__ void warp_scan_level(DevP p, WarpSegArgs a, const cplx* __restrict__ in, cplx* __restrict__ out, int off, int spb) {
+__global__ void warp_scan_level(DevP p, WarpSegArgs a, const cplx* __restrict__ in, cplx* __restrict__ out, int off, int R, int spb) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int N = p.N, NN = N * N, G = p.G;
     const int sub = threadIdx.x / W, r = threadIdx.x % W;
@@ -263,12 +266,20 @@ __global__ void warp_scan_level(DevP p, WarpSegArgs a, const cplx* __restrict__ 
         for (int e = r; e < NN; e += W) o[e] = x[e];
         return;
     }
-    cplx* A = reinterpret_cast<cplx*>(smraw) + (size_t)sub * 2 * NN;
-    cplx* B = A + NN;
-    const cplx* y = in + ((size_t)(seg - off) * G + g) * NN;
-    for (int e = r; e < NN; e += W) { A[e] = x[e]; B[e] = y[e]; }
+    cplx* buf = reinterpret_cast<cplx*>(smraw) + (size_t)sub * (R + 1) * NN;   // R operands + one spare
+    const int cnt = min(R, seg / off + 1);                                      // factors x_seg, x_{seg-off}, ..
+    for (int j = 0; j < cnt; ++j) {
+        const cplx* y = in + ((size_t)(seg - j * off) * G + g) * NN;
+        for (int e = r; e < NN; e += W) buf[(size_t)j * NN + e] = y[e];
+    }
     __syncwarp(mask);
-    sw_matmul<W>(o, A, B, N, r, mask);
+    // t = x_seg; t <- t x_{seg - j off}: products go to the spare buffer, then to operand buffers that are done
+    const cplx* t = buf;
+    for (int j = 1; j < cnt; ++j) {
+        cplx* c = j == cnt - 1 ? o : (j == 1 ? buf + (size_t)R * NN : buf + (size_t)(j - 2) * NN);
+        sw_matmul<W>(c, t, buf + (size_t)j * NN, N, r, mask);
+        t = c;
+    }
 }
 
 // Psi_k at every segment end from the prefix products, tau_k from the last one; unit = (k, seg)
@@ -374,7 +385,12 @@ inline int warp_seg_setup(WarpSegArgs& a, const WarpPlan& wp, const DevP& p, con
         check(d->Hc, (size_t)p.G * p.L);
     }
     a.scan = herm && p.NT >= 16 && !(getenv("GRAPE_B200_WSEG_SCAN") && atoi(getenv("GRAPE_B200_WSEG_SCAN")) == 0);
-    if (a.scan) S = std::max(2, (p.NT + 127) / 128);   // <= 128 segments: one sub-warp per segment for W = 8
+    // radix-4 levels where five N x N matrices per sub-warp fit the shared memory of a block (N <= 16)
+    a.radix = ((size_t)5 * p.N * p.N * sizeof(cplx) * (128 / wp.W) <= 200 * 1024) ? 4 : 2;
+    if (const char* e = getenv("GRAPE_B200_WSEG_RADIX")) a.radix = atoi(e) == 4 && a.radix == 4 ? 4 : 2;
+    // without chains the segment count only costs scan levels: 256 segments (measured on C2: S = 8 0.146 ms, 12: 0.152,
+    // 16: 0.159, 24: 0.179 with radix-2 levels, profiles/r2_s24_bench_c2_*.json)
+    if (a.scan) S = std::max(2, (p.NT + 255) / 256);
     if (const char* e = getenv("GRAPE_B200_SEG_S")) S = atoi(e);
     a.S = S < 2 ? 2 : (S > 128 ? 128 : S);
     a.NSEG = (p.NT + a.S - 1) / a.S;
@@ -392,7 +408,7 @@ inline int warp_seg_setup(WarpSegArgs& a, const WarpPlan& wp, const DevP& p, con
             *dst = static_cast<cplx*>(q);
         }
         int levels = 0;
-        for (int off = 1; off < a.NSEG; off <<= 1) ++levels;
+        for (int off = 1; off < a.NSEG; off *= a.radix) ++levels;
         a.Q = levels == 0 ? a.Pseg : ((levels & 1) ? a.Qa : a.Qb);
     }
     cudaError_t e = cudaSuccess;
@@ -400,7 +416,7 @@ inline int warp_seg_setup(WarpSegArgs& a, const WarpPlan& wp, const DevP& p, con
     const size_t smem = (size_t)(3 + a.pf) * p.N * p.N * sizeof(cplx) * (128 / wp.W);
     WARP_SWITCH(wp.W, e = cudaFuncSetAttribute(warp_segprod<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
     if (e == cudaSuccess && a.scan) {
-        const size_t smem2 = (size_t)2 * p.N * p.N * sizeof(cplx) * (128 / wp.W);
+        const size_t smem2 = (size_t)(a.radix + 1) * p.N * p.N * sizeof(cplx) * (128 / wp.W);
         WARP_SWITCH(wp.W, e = cudaFuncSetAttribute(warp_scan_level<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2))
     }
     if (e != cudaSuccess) { err = std::string("cudaFuncSetAttribute failed (warp seg): ") + cudaGetErrorString(e); return GRAPE_B200_ECUDA; }
@@ -414,11 +430,11 @@ inline void warp_seg_run_prod(const WarpSegArgs& a, const WarpPlan& wp, const De
     WARP_SWITCH(wp.W, warp_segprod<WW><<<(unsigned)((units + spb - 1) / spb), 128, smem, st>>>(p, a, spb, a.pf))
     launches++;
     if (a.scan) {
-        const size_t smem2 = (size_t)2 * p.N * p.N * sizeof(cplx) * spb;
+        const size_t smem2 = (size_t)(a.radix + 1) * p.N * p.N * sizeof(cplx) * spb;
         const cplx* in = a.Pseg;
         cplx* out = a.Qa;
-        for (int off = 1; off < a.NSEG; off <<= 1) {
-            WARP_SWITCH(wp.W, warp_scan_level<WW><<<(unsigned)((units + spb - 1) / spb), 128, smem2, st>>>(p, a, in, out, off, spb))
+        for (int off = 1; off < a.NSEG; off *= a.radix) {
+            WARP_SWITCH(wp.W, warp_scan_level<WW><<<(unsigned)((units + spb - 1) / spb), 128, smem2, st>>>(p, a, in, out, off, a.radix, spb))
             launches++;
             in = out;
             out = out == a.Qa ? a.Qb : a.Qa;

@@ -179,3 +179,22 @@ def test_economised_polynomial_table(lib_built):
     g12 = (C.c_double * 13)()
     lib.grape_b200_econ_table(12, C.byref(th12), g12)
     assert th12.value >= 0.525   # C4 / C5: ||H_n dt|| <= 0.525 -> degree 12 = four 3-term stages (Taylor: 15..16)
+
+
+def test_flops_model_follows_the_series_tables(lib_built, monkeypatch):
+    """grape.jl_b200/peaks.py (the executed-flops model behind `roofline.achieved`) mirrors the kernels' plans: with the
+    economised series C3 takes 5 orders per gradient step and C4 degree 12 per dense step; GRAPE_B200_ECON=0 gives the
+    Taylor orders (7 resp. 15..16)."""
+    from grape.jl_b200 import configs, peaks
+    p3, e3 = configs.c3_ensemble(n_delta=8, n_amp=8)
+    p4, e4 = configs.c4_dense450(N=64, K=16, NT=40)
+    monkeypatch.delenv("GRAPE_B200_ECON", raising=False)
+    econ3 = peaks.executed_flops_split(p3, e3, schedule=3)
+    econ4 = peaks.dense_flops_per_unit(p4, e4, 1)[3]
+    monkeypatch.setenv("GRAPE_B200_ECON", "0")
+    tay3 = peaks.executed_flops_split(p3, e3, schedule=3)
+    tay4 = peaks.dense_flops_per_unit(p4, e4, 1)[3]
+    assert econ3["contraction"] < 0.85 * tay3["contraction"] and econ3["formation"] <= tay3["formation"]
+    assert 10.0 <= econ4 <= 12.0 and 13.0 <= tay4 <= 16.0
+    th = peaks.econ_theta()
+    assert th[12] >= 0.525 and th[5] >= 0.0065 and all(th[m] <= th[m + 1] for m in range(2, 20))

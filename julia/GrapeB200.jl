@@ -257,6 +257,20 @@ function chi_states(b::B200Workspace)
     return [chi[:, k] for k in 1:b.K], rho
 end
 
+"""
+    dense_orders(b) -> (economised::Bool, orders::Vector{Int32})
+
+Polynomial degree of every time step in the last call of the dense path (N > 32). `economised` is true when the
+chains summed the Chebyshev-cut polynomial of `exp(-i H dt)` -- what `prop_method = Cheby` is in the reference
+(docs/src/tutorial.md:308, 432) -- which the library selects by itself for Hermitian generators.
+"""
+function dense_orders(b::B200Workspace)
+    orders = zeros(Int32, b.NT)
+    rc = ccall((:grape_b200_dense_orders, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), b.handle, orders)
+    rc < 0 && _check(-rc, b.handle)
+    return rc == 1, orders
+end
+
 # ------------------------------------------------------------------------------------------------------------
 # Several GPUs from this one Julia process (the reference threads over trajectories, src/optimize.jl:720, 876):
 # `grape_b200_multi_create` splits the trajectories into contiguous blocks, one per device; the shards reduce the
